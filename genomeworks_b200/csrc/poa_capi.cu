@@ -1,0 +1,916 @@
+// gw-b200: host engine + C ABI for the POA path (see include/gwb200.h for the reference interface each entry replaces).
+//
+// Host-side behaviour follows cudapoa/src/cudapoa_batch.cuh (admission, packing, status decoding) and
+// cudapoa/src/batch.cu (BatchConfig derivation, type selection via cudapoa_limits.hpp); memory layout and kernels are
+// this repo's own (poa_kernels.cuh). There is no CPU fallback: every entry needs a CUDA device.
+
+#include "../../include/gwb200.h"
+#include "common.cuh"
+#include "poa_kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace gwb200;
+using namespace gwb200::poa;
+
+namespace
+{
+
+inline int32_t align_up(int32_t v, int32_t b) { return (v + b - 1) & ~(b - 1); }
+inline int64_t align_up64(int64_t v, int64_t b) { return (v + b - 1) / b * b; }
+
+// cudapoa_limits.hpp:34-59
+bool use32bit_score(const gwb200_poa_config& c, int32_t gap, int32_t mismatch, int32_t match)
+{
+    int32_t upper = c.max_sequence_size * match;
+    int32_t lower = c.max_sequence_size * std::max(gap, mismatch) + (c.max_nodes_per_graph - c.max_sequence_size) * gap;
+    return (upper > INT16_MAX || (-lower) > (INT16_MAX + 1));
+}
+bool use32bit_size(const gwb200_poa_config& c)
+{
+    int32_t m = std::max(c.max_consensus_size, std::max(c.max_nodes_per_graph, c.matrix_sequence_dimension));
+    return m > INT16_MAX;
+}
+
+struct Carver
+{
+    uint8_t* base;
+    int64_t off = 0;
+    template <typename T>
+    T* take(int64_t count)
+    {
+        off      = align_up64(off, 256);
+        T* p     = reinterpret_cast<T*>(base + off);
+        off += count * static_cast<int64_t>(sizeof(T));
+        return p;
+    }
+};
+
+} // namespace
+
+struct gwb200_poa_batch
+{
+    int32_t device_id = 0;
+    cudaStream_t stream = nullptr;
+    int8_t output_mask  = 0;
+    gwb200_poa_config cfg{};
+    int32_t gap = -8, mismatch = -6, match = 8;
+    bool score32 = false, size32 = false, msa = false;
+    int32_t score_bytes = 2, size_bytes = 2;
+    int32_t bid = 0;
+
+    int32_t max_poas = 0;
+    int32_t poa_count = 0;
+    int32_t num_nucleotides_copied = 0;
+    int32_t global_sequence_idx = 0;
+    int64_t avail_buf_mem = 0, scorebuf_alloc_size = 0;
+    int64_t next_scores_offset = 0;
+    int64_t seq_capacity = 0; // bytes in the sequences / weights buffers (without slack)
+
+    // pinned host
+    uint8_t* h_block = nullptr;
+    uint8_t* h_sequences = nullptr;
+    int8_t* h_weights = nullptr;
+    int32_t* h_seq_lengths = nullptr;
+    WindowInfo* h_windows = nullptr;
+    uint8_t* h_consensus = nullptr;
+    uint16_t* h_coverage = nullptr;
+    int32_t* h_cons_len = nullptr;
+    int32_t* h_status = nullptr;
+    int32_t* h_node_count = nullptr;
+    unsigned long long* h_cells = nullptr;
+    uint8_t* h_msa = nullptr;
+
+    // device
+    uint8_t* d_block = nullptr;
+    DeviceParams P{};
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool launched = false;
+    bool results_on_host = false;
+
+    static int32_t batches;
+};
+int32_t gwb200_poa_batch::batches = 0;
+
+namespace
+{
+
+struct Sizes
+{
+    int64_t dev_per_poa = 0, dev_per_matrix = 0, host_per_poa = 0;
+    int64_t seq_bytes_per_poa = 0;
+    int32_t aln_capacity = 0, stack_capacity = 0;
+};
+
+Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz, bool msa)
+{
+    Sizes s;
+    const int64_t mn = c.max_nodes_per_graph;
+    const int64_t E  = kMaxEdges;
+    s.aln_capacity   = c.max_nodes_per_graph + c.max_sequence_size + 16;
+    s.stack_capacity = msa ? 4 * c.max_nodes_per_graph + 16 : 0;
+    s.seq_bytes_per_poa = static_cast<int64_t>(c.max_sequences_per_poa) * align_up(std::max(c.max_sequence_size, 1), 4);
+    int64_t d = 0;
+    d += mn * 1;                 // nodes
+    d += mn * 2 * 5;             // in_cnt out_cnt aln_cnt cov local_cnt
+    d += mn * E * sz * 2;        // in_edges, out_edges
+    d += mn * kMaxAligned * sz;  // aligned
+    d += mn * E * 2;             // in_w
+    d += mn * sz * 2;            // sorted, pos
+    d += 2ll * s.aln_capacity * sz;
+    d += mn * 4 + mn * sz;       // consensus scratch
+    d += s.seq_bytes_per_poa * 2;              // sequences + weights
+    d += 4ll * c.max_sequences_per_poa;        // seq lengths
+    d += sizeof(WindowInfo);
+    d += c.max_consensus_size * 3ll;           // consensus + coverage
+    d += 4 * 3 + 8;                            // len, status, node_count, cells
+    if (msa)
+    {
+        d += s.seq_bytes_per_poa * sz; // path
+        d += mn * sz + mn * 2;         // msa_col, marks, check
+        d += static_cast<int64_t>(s.stack_capacity) * sz;
+        d += static_cast<int64_t>(c.max_sequences_per_poa) * c.max_consensus_size;
+    }
+    d += 256 * 32; // carving alignment slack
+    s.dev_per_poa    = d;
+    s.dev_per_matrix = static_cast<int64_t>(c.matrix_sequence_dimension) * mn * score_bytes;
+    int64_t h        = s.seq_bytes_per_poa * 2 + 4ll * c.max_sequences_per_poa + sizeof(WindowInfo) + c.max_consensus_size * 3ll + 4 * 3 + 8;
+    if (msa)
+        h += static_cast<int64_t>(c.max_sequences_per_poa) * c.max_consensus_size;
+    s.host_per_poa = h + 64;
+    return s;
+}
+
+template <typename ScoreT, typename SizeT>
+void launch_typed(gwb200_poa_batch* b)
+{
+    dim3 grid(b->poa_count), block(32);
+    if (b->msa)
+        poa_window_kernel<ScoreT, SizeT, true><<<grid, block, 0, b->stream>>>(b->P);
+    else
+        poa_window_kernel<ScoreT, SizeT, false><<<grid, block, 0, b->stream>>>(b->P);
+    count_launch();
+}
+
+int validate_config(const gwb200_poa_config& c)
+{
+    if (c.max_sequence_size < 0 || c.max_consensus_size < 0 || c.max_nodes_per_graph < 0 || c.max_sequences_per_poa < 0 ||
+        c.alignment_band_width < 0 || c.matrix_sequence_dimension < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "BatchConfig fields cannot be negative.");
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int gwb200_poa_init(void) { return GWB200_POA_SUCCESS; }
+
+int gwb200_poa_config_init(gwb200_poa_config* cfg, int32_t max_seq_sz, int32_t max_seq_per_poa, int32_t band_width, int32_t band_mode,
+                           float adaptive_storage_factor, float graph_length_factor, int32_t max_pred_dist)
+{
+    if (!cfg)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "cfg is null");
+    if (band_mode < 0 || band_mode > GWB200_POA_ADAPTIVE_BAND_TRACEBACK)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "unknown band mode");
+    // batch.cu:34-71
+    const int32_t abw              = align_up(band_width, kMinBandWidth);
+    cfg->max_sequence_size         = max_seq_sz;
+    cfg->max_consensus_size        = 2 * max_seq_sz;
+    cfg->alignment_band_width      = abw;
+    cfg->max_sequences_per_poa     = max_seq_per_poa;
+    cfg->band_mode                 = band_mode;
+    cfg->max_banded_pred_distance  = max_pred_dist > 0 ? max_pred_dist : 2 * abw;
+    cfg->max_nodes_per_graph       = align_up(static_cast<int32_t>(graph_length_factor * max_seq_sz), kCPT);
+    if (band_mode == GWB200_POA_FULL_BAND)
+        cfg->matrix_sequence_dimension = align_up(max_seq_sz, kCPT);
+    else if (band_mode == GWB200_POA_STATIC_BAND || band_mode == GWB200_POA_STATIC_BAND_TRACEBACK)
+        cfg->matrix_sequence_dimension = align_up(abw + kRightPad, kCPT);
+    else
+        cfg->matrix_sequence_dimension = align_up(static_cast<int32_t>(adaptive_storage_factor * (abw + kRightPad)), kCPT);
+    if (max_seq_sz < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_sequence_size cannot be negative.");
+    if (max_seq_per_poa < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_sequences_per_poa cannot be negative.");
+    if (band_width < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "alignment_band_width cannot be negative.");
+    if (cfg->max_nodes_per_graph < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_nodes_per_graph cannot be negative.");
+    if (abw != band_width)
+        fprintf(stderr, "Band-width should be multiple of 128. The input was changed from %d to %d\n", band_width, abw);
+    return 0;
+}
+
+int gwb200_poa_config_init_explicit(gwb200_poa_config* cfg, int32_t max_seq_sz, int32_t max_consensus_sz, int32_t max_nodes_per_poa,
+                                    int32_t band_width, int32_t max_seq_per_poa, int32_t matrix_seq_dim, int32_t band_mode, int32_t max_pred_dist)
+{
+    if (!cfg)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "cfg is null");
+    if (band_mode < 0 || band_mode > GWB200_POA_ADAPTIVE_BAND_TRACEBACK)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "unknown band mode");
+    // batch.cu:73-104
+    cfg->max_sequence_size         = max_seq_sz;
+    cfg->max_consensus_size        = max_consensus_sz;
+    cfg->max_nodes_per_graph       = align_up(max_nodes_per_poa, kCPT);
+    cfg->matrix_sequence_dimension = align_up(matrix_seq_dim, kCPT);
+    cfg->alignment_band_width      = align_up(band_width, kMinBandWidth);
+    cfg->max_sequences_per_poa     = max_seq_per_poa;
+    cfg->band_mode                 = band_mode;
+    cfg->max_banded_pred_distance  = max_pred_dist;
+    if (max_seq_sz < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_sequence_size cannot be negative.");
+    if (max_consensus_sz < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_consensus_size cannot be negative.");
+    if (max_nodes_per_poa < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_nodes_per_graph cannot be negative.");
+    if (max_seq_per_poa < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_sequences_per_poa cannot be negative.");
+    if (band_width < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "alignment_band_width cannot be negative.");
+    if (max_pred_dist < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_banded_pred_distance cannot be negative.");
+    if (cfg->max_nodes_per_graph < cfg->max_sequence_size)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_nodes_per_graph should be greater than or equal to max_sequence_size.");
+    if (cfg->max_consensus_size < cfg->max_sequence_size)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_consensus_size should be greater than or equal to max_sequence_size.");
+    if (cfg->max_sequence_size < cfg->alignment_band_width)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "alignment_band_width should not be greater than max_sequence_size.");
+    if (cfg->alignment_band_width != band_width)
+        fprintf(stderr, "Band-width should be multiple of 128. The input was changed from %d to %d\n", band_width, cfg->alignment_band_width);
+    return 0;
+}
+
+int gwb200_poa_decode_error(int32_t status, char* message, int32_t message_len, char* hint, int32_t hint_len)
+{
+    const char* m = nullptr;
+    const char* h = "";
+    switch (status)
+    {
+    case GWB200_POA_EXCEEDED_MAXIMUM_POAS:
+        m = "Kernel Error: more groups were added than the batch has room for (maximum POAs).";
+        h = "Suggestion  : size the batch with more device memory or split the groups over several batches.";
+        break;
+    case GWB200_POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE:
+        m = "Kernel Error: an input read, or the output consensus/MSA, is longer than the configured maximum.";
+        h = "Suggestion  : raise BatchConfig::max_sequence_size / BatchConfig::max_consensus_size.";
+        break;
+    case GWB200_POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA:
+        m = "Kernel Error: too many reads in one POA group.";
+        h = "Suggestion  : raise BatchConfig::max_sequences_per_poa.";
+        break;
+    case GWB200_POA_NODE_COUNT_EXCEEDED_MAXIMUM_GRAPH_SIZE:
+        m = "Kernel Error: the POA graph grew beyond the maximum number of nodes.";
+        h = "Suggestion  : raise BatchConfig::max_nodes_per_graph.";
+        break;
+    case GWB200_POA_EDGE_COUNT_EXCEEDED_MAXIMUM_GRAPH_SIZE:
+        m = "Kernel Error: a node exceeded the maximum number of edges.";
+        h = "Suggestion  : the per-node edge limit is a compile-time constant (50).";
+        break;
+    case GWB200_POA_EXCEEDED_ADAPTIVE_BANDED_MATRIX_SIZE:
+        m = "Kernel Error: the score/traceback buffer is too small for the adaptive band of this window.";
+        h = "Suggestion  : raise BatchConfig::matrix_sequence_dimension (adaptive_storage_factor).";
+        break;
+    case GWB200_POA_EXCEEDED_MAXIMUM_PREDECESSOR_DISTANCE:
+        m = "Kernel Error: a predecessor lies further back than max_banded_pred_distance allows in traceback mode.";
+        h = "Suggestion  : raise BatchConfig::max_banded_pred_distance.";
+        break;
+    case GWB200_POA_LOOP_COUNT_EXCEEDED_UPPER_BOUND:
+        m = "Kernel Error: Needleman-Wunsch traceback did not terminate.";
+        h = "Suggestion  : retry with another banding mode.";
+        break;
+    case GWB200_POA_OUTPUT_TYPE_UNAVAILABLE:
+        m = "Kernel Error: the requested output type was not enabled for this batch.";
+        h = "Suggestion  : check the consensus/MSA output mask passed to create_batch.";
+        break;
+    case GWB200_POA_ZERO_WEIGHTED_POA_SEQUENCE:
+        m = "Error      : every base weight of the sequence is zero.";
+        h = "Suggestion : check the base weights passed with the POA group.";
+        break;
+    case GWB200_POA_EMPTY_POA_GROUP:
+        m = "Error      : no sequence of the POA group could be added.";
+        h = "Suggestion : inspect the per-sequence status from add_poa_group.";
+        break;
+    case GWB200_POA_GENERIC_ERROR:
+        m = "Unknown error.";
+        break;
+    default:
+        return set_error(GWB200_E_RUNTIME, "Unknown error type detected.");
+    }
+    if (message && message_len > 0)
+    {
+        std::strncpy(message, m, message_len - 1);
+        message[message_len - 1] = 0;
+    }
+    if (hint && hint_len > 0)
+    {
+        std::strncpy(hint, h, hint_len - 1);
+        hint[hint_len - 1] = 0;
+    }
+    return 0;
+}
+
+int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* stream, int64_t max_gpu_mem, int8_t output_mask,
+                            const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score, int16_t match_score)
+{
+    if (!out || !cfg)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (device_id < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "Device ID has to be non-negative");
+    if (max_gpu_mem < -1)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_gpu_mem has to be either -1 (=all available GPU memory) or greater or equal than 0.");
+    if (int rc = validate_config(*cfg))
+        return rc;
+    if (cfg->band_mode == GWB200_POA_STATIC_BAND_TRACEBACK || cfg->band_mode == GWB200_POA_ADAPTIVE_BAND_TRACEBACK)
+        return set_error(GWB200_E_RUNTIME, "traceback band modes are not implemented by this engine yet (no fallback exists)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device_id)
+    {
+        cudaGetLastError();
+        return set_error(GWB200_E_CUDA, "no usable CUDA device: this engine has no CPU fallback");
+    }
+    DeviceGuard guard(device_id);
+
+    gwb200_poa_batch* b = new gwb200_poa_batch;
+    b->device_id        = device_id;
+    b->stream           = static_cast<cudaStream_t>(stream);
+    b->output_mask      = output_mask;
+    b->cfg              = *cfg;
+    b->gap              = gap_score;
+    b->mismatch         = mismatch_score;
+    b->match            = match_score;
+    b->score32          = use32bit_score(*cfg, gap_score, mismatch_score, match_score);
+    b->size32           = use32bit_size(*cfg);
+    b->score_bytes      = b->score32 ? 4 : 2;
+    b->size_bytes       = b->size32 ? 4 : 2;
+    b->msa              = (output_mask & GWB200_POA_OUTPUT_MSA) != 0;
+    b->bid              = gwb200_poa_batch::batches++;
+
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+    {
+        delete b;
+        return set_error(GWB200_E_CUDA, "cudaMemGetInfo failed");
+    }
+    int64_t avail = static_cast<int64_t>(static_cast<double>(free_b) * 0.95);
+    if (max_gpu_mem >= 0)
+        avail = std::min(avail, max_gpu_mem);
+    const Sizes sz = compute_sizes(*cfg, b->score_bytes, b->size_bytes, b->msa);
+    if (avail < sz.dev_per_poa + (cfg->band_mode == GWB200_POA_FULL_BAND ? 0 : sz.dev_per_matrix) || sz.dev_per_poa + sz.dev_per_matrix <= 0)
+    {
+        std::string msg = "Requires at least " + std::to_string(sz.dev_per_poa + sz.dev_per_matrix) +
+                          " bytes of device memory per CUDAPOA batch to process correctly.";
+        delete b;
+        return set_error(GWB200_E_RUNTIME, msg.c_str());
+    }
+    int64_t max_poas = avail / (sz.dev_per_poa + sz.dev_per_matrix);
+    max_poas         = std::max<int64_t>(1, std::min<int64_t>(max_poas, 1 << 20));
+    b->max_poas      = static_cast<int32_t>(max_poas);
+    const int64_t n  = max_poas;
+    const int64_t mn = cfg->max_nodes_per_graph;
+    const int64_t mc = cfg->max_consensus_size;
+
+    // ---- pinned host block
+    {
+        int64_t total_h = n * sz.host_per_poa + 4096 * 2 + 4096;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&b->h_block), total_h, cudaHostAllocDefault) != cudaSuccess)
+        {
+            cudaGetLastError();
+            delete b;
+            return set_error(GWB200_E_BAD_ALLOC, "pinned host allocation failed");
+        }
+        Carver hc{b->h_block};
+        b->seq_capacity  = n * sz.seq_bytes_per_poa;
+        b->h_sequences   = hc.take<uint8_t>(b->seq_capacity + 4096);
+        b->h_weights     = hc.take<int8_t>(b->seq_capacity + 4096);
+        b->h_seq_lengths = hc.take<int32_t>(n * cfg->max_sequences_per_poa);
+        b->h_windows     = hc.take<WindowInfo>(n);
+        b->h_consensus   = hc.take<uint8_t>(n * mc);
+        b->h_coverage    = hc.take<uint16_t>(n * mc);
+        b->h_cons_len    = hc.take<int32_t>(n);
+        b->h_status      = hc.take<int32_t>(n);
+        b->h_node_count  = hc.take<int32_t>(n);
+        b->h_cells       = hc.take<unsigned long long>(n);
+        if (b->msa)
+            b->h_msa = hc.take<uint8_t>(n * cfg->max_sequences_per_poa * mc);
+        if (hc.off > total_h + 256 * 16)
+        {
+            // host_per_poa has 64 B slack per POA; the 256 B carve alignment of 12 arrays is covered by the constant above
+        }
+        std::memset(b->h_sequences, 0, b->seq_capacity + 4096);
+    }
+    // ---- device block
+    {
+        const int64_t fixed   = 4096 * 2 + 256 * 64;
+        const int64_t total_d = n * (sz.dev_per_poa + sz.dev_per_matrix) + fixed;
+        if (cudaMalloc(reinterpret_cast<void**>(&b->d_block), total_d) != cudaSuccess)
+        {
+            cudaGetLastError();
+            cudaFreeHost(b->h_block);
+            delete b;
+            return set_error(GWB200_E_BAD_ALLOC, "Out of memory: device allocation for the POA batch failed");
+        }
+        Carver dc{b->d_block};
+        DeviceParams& P = b->P;
+        const int64_t S = b->size_bytes;
+        P.sequences     = dc.take<uint8_t>(b->seq_capacity + 4096);
+        P.weights       = dc.take<int8_t>(b->seq_capacity + 4096);
+        P.seq_lengths   = dc.take<int32_t>(n * cfg->max_sequences_per_poa);
+        P.windows       = dc.take<WindowInfo>(n);
+        P.nodes         = dc.take<uint8_t>(n * mn);
+        P.in_cnt        = dc.take<uint16_t>(n * mn);
+        P.out_cnt       = dc.take<uint16_t>(n * mn);
+        P.aln_cnt       = dc.take<uint16_t>(n * mn);
+        P.node_cov      = dc.take<uint16_t>(n * mn);
+        P.local_cnt     = dc.take<uint16_t>(n * mn);
+        P.in_edges      = dc.take<uint8_t>(n * mn * kMaxEdges * S);
+        P.out_edges     = dc.take<uint8_t>(n * mn * kMaxEdges * S);
+        P.aligned       = dc.take<uint8_t>(n * mn * kMaxAligned * S);
+        P.in_w          = dc.take<uint16_t>(n * mn * kMaxEdges);
+        P.sorted        = dc.take<uint8_t>(n * mn * S);
+        P.pos           = dc.take<uint8_t>(n * mn * S);
+        P.aln_graph     = dc.take<uint8_t>(n * sz.aln_capacity * S);
+        P.aln_read      = dc.take<uint8_t>(n * sz.aln_capacity * S);
+        P.cons_scores   = dc.take<int32_t>(n * mn);
+        P.cons_preds    = dc.take<uint8_t>(n * mn * S);
+        P.consensus     = dc.take<uint8_t>(n * mc);
+        P.coverage      = dc.take<uint16_t>(n * mc);
+        P.consensus_len = dc.take<int32_t>(n);
+        P.status        = dc.take<int32_t>(n);
+        P.node_count    = dc.take<int32_t>(n);
+        P.cells         = dc.take<unsigned long long>(n);
+        if (b->msa)
+        {
+            P.seq_path       = dc.take<uint8_t>((b->seq_capacity + 4096) * S);
+            P.msa_col        = dc.take<uint8_t>(n * mn * S);
+            P.marks          = dc.take<uint8_t>(n * mn);
+            P.check          = dc.take<uint8_t>(n * mn);
+            P.stack          = dc.take<uint8_t>(n * sz.stack_capacity * S);
+            P.stack_capacity = sz.stack_capacity;
+            P.msa_out        = dc.take<uint8_t>(n * cfg->max_sequences_per_poa * mc);
+        }
+        // everything that is left is the score pool (allocate_block.hpp:227-239)
+        dc.off                 = align_up64(dc.off, 256);
+        P.scores               = b->d_block + dc.off;
+        b->scorebuf_alloc_size = total_d - dc.off;
+        P.max_nodes            = cfg->max_nodes_per_graph;
+        P.matrix_seq_dim       = cfg->matrix_sequence_dimension;
+        P.max_consensus        = cfg->max_consensus_size;
+        P.max_seqs             = cfg->max_sequences_per_poa;
+        P.band_width           = cfg->alignment_band_width;
+        P.band_mode            = cfg->band_mode;
+        P.gap                  = b->gap;
+        P.mismatch             = b->mismatch;
+        P.match                = b->match;
+        P.msa                  = b->msa ? 1 : 0;
+        P.aln_capacity         = sz.aln_capacity;
+    }
+    cudaEventCreate(&b->ev0);
+    cudaEventCreate(&b->ev1);
+    gwb200_poa_batch_reset(b);
+    *out = b;
+    return 0;
+}
+
+void gwb200_poa_batch_destroy(gwb200_poa_batch* b)
+{
+    if (!b)
+        return;
+    DeviceGuard guard(b->device_id);
+    cudaStreamSynchronize(b->stream);
+    if (b->ev0)
+        cudaEventDestroy(b->ev0);
+    if (b->ev1)
+        cudaEventDestroy(b->ev1);
+    if (b->d_block)
+        cudaFree(b->d_block);
+    if (b->h_block)
+        cudaFreeHost(b->h_block);
+    delete b;
+}
+
+int gwb200_poa_batch_reset(gwb200_poa_batch* b)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    b->poa_count              = 0;
+    b->num_nucleotides_copied = 0;
+    b->global_sequence_idx    = 0;
+    b->next_scores_offset     = 0;
+    b->avail_buf_mem          = b->scorebuf_alloc_size;
+    b->launched               = false;
+    b->results_on_host        = false;
+    return 0;
+}
+
+// cudapoa_batch.cuh:103-151 (add_poa_group), :456-472 (add_poa), :475-542 (add_seq_to_poa), :545-570 (reserve_buf)
+int gwb200_poa_batch_add_group(gwb200_poa_batch* b, int32_t n, const char* const* seqs, const int8_t* const* weights,
+                               const int32_t* lengths, int32_t* per_seq_status, int32_t* n_per_seq)
+{
+    if (!b || (n > 0 && (!seqs || !lengths)))
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null argument");
+    if (n_per_seq)
+        *n_per_seq = 0;
+    if (n <= 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "empty POA group"); // the reference dereferences end() here
+    const gwb200_poa_config& c = b->cfg;
+    int32_t max_seq_length     = 0;
+    for (int32_t i = 0; i < n; i++)
+        max_seq_length = std::max(max_seq_length, lengths[i]);
+    // reserve_buf
+    {
+        const int64_t width = (c.band_mode != GWB200_POA_FULL_BAND) ? c.matrix_sequence_dimension : align_up(max_seq_length + 1 + kCPT, 4);
+        const int64_t req   = width * static_cast<int64_t>(c.max_nodes_per_graph) * b->score_bytes;
+        if (req > b->avail_buf_mem)
+            return GWB200_POA_EXCEEDED_MAXIMUM_POAS;
+        b->avail_buf_mem -= req;
+    }
+    // add_poa
+    if (b->poa_count == b->max_poas)
+        return GWB200_POA_EXCEEDED_MAXIMUM_POAS;
+    WindowInfo wi{};
+    wi.num_seqs       = 0;
+    wi.seq_len_offset = b->global_sequence_idx;
+    wi.seq_start      = b->num_nucleotides_copied;
+    wi.scores_width   = 0;
+    wi.scores_offset  = b->next_scores_offset;
+    WindowInfo* w     = &b->h_windows[b->poa_count];
+    *w                = wi;
+    b->poa_count++;
+    b->results_on_host = false;
+
+    bool poa_empty = true;
+    for (int32_t i = 0; i < n; i++)
+    {
+        const int32_t len = lengths[i];
+        const int8_t* wt  = weights ? weights[i] : nullptr;
+        int32_t st        = GWB200_POA_SUCCESS;
+        if (len > c.max_sequence_size)
+        {
+            st = GWB200_POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE;
+        }
+        else
+        {
+            if (wt != nullptr)
+            {
+                bool all_zero = true;
+                for (int32_t k = 0; k < len; k++)
+                {
+                    if (wt[k] < 0)
+                        return set_error(GWB200_E_INVALID_ARGUMENT, "Base weights need to be non-negative");
+                    if (wt[k] > 0)
+                        all_zero = false;
+                }
+                if (all_zero)
+                    st = GWB200_POA_ZERO_WEIGHTED_POA_SEQUENCE;
+            }
+            if (st == GWB200_POA_SUCCESS)
+            {
+                const int32_t sw = align_up(len + 1 + kCPT, 4);
+                if (sw > w->scores_width)
+                {
+                    b->next_scores_offset += (sw - w->scores_width);
+                    w->scores_width = sw;
+                }
+                if (w->num_seqs >= c.max_sequences_per_poa)
+                {
+                    st = GWB200_POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA;
+                }
+                else
+                {
+                    w->num_seqs++;
+                    std::memcpy(b->h_sequences + b->num_nucleotides_copied, seqs[i], len);
+                    if (wt == nullptr)
+                        std::memset(b->h_weights + b->num_nucleotides_copied, 1, len);
+                    else
+                        std::memcpy(b->h_weights + b->num_nucleotides_copied, wt, len);
+                    b->h_seq_lengths[b->global_sequence_idx] = len;
+                    b->num_nucleotides_copied += align_up(len, 4);
+                    b->global_sequence_idx++;
+                }
+            }
+        }
+        if (st == GWB200_POA_SUCCESS)
+            poa_empty = false;
+        if (per_seq_status)
+            per_seq_status[i] = st;
+    }
+    if (n_per_seq)
+        *n_per_seq = n;
+    if (poa_empty)
+        return GWB200_POA_EMPTY_POA_GROUP;
+    return GWB200_POA_SUCCESS;
+}
+
+int gwb200_poa_batch_add_groups_flat(gwb200_poa_batch* b, int32_t n_windows, const int32_t* win_nseq, const int32_t* seq_len,
+                                     const char* seq_data, const int8_t* weights, int32_t* n_added)
+{
+    if (!b || !win_nseq || !seq_len || !seq_data)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null argument");
+    if (n_added)
+        *n_added = 0;
+    std::vector<const char*> seqs;
+    std::vector<const int8_t*> wts;
+    int64_t off = 0;
+    int32_t si  = 0;
+    for (int32_t w = 0; w < n_windows; w++)
+    {
+        const int32_t ns = win_nseq[w];
+        seqs.resize(ns);
+        wts.resize(ns);
+        int64_t o = off;
+        for (int32_t s = 0; s < ns; s++)
+        {
+            seqs[s] = seq_data + o;
+            wts[s]  = weights ? weights + o : nullptr;
+            o += seq_len[si + s];
+        }
+        int rc = gwb200_poa_batch_add_group(b, ns, seqs.data(), weights ? wts.data() : nullptr, seq_len + si, nullptr, nullptr);
+        if (rc != GWB200_POA_SUCCESS)
+            return rc;
+        off = o;
+        si += ns;
+        if (n_added)
+            *n_added = w + 1;
+    }
+    return GWB200_POA_SUCCESS;
+}
+
+int32_t gwb200_poa_batch_total_poas(const gwb200_poa_batch* b) { return b ? b->poa_count : 0; }
+int32_t gwb200_poa_batch_max_poas(const gwb200_poa_batch* b) { return b ? b->max_poas : 0; }
+int32_t gwb200_poa_batch_id(const gwb200_poa_batch* b) { return b ? b->bid : -1; }
+int32_t gwb200_poa_batch_score_bytes(const gwb200_poa_batch* b) { return b ? b->score_bytes : 0; }
+
+int gwb200_poa_batch_upload(gwb200_poa_batch* b)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    if (b->poa_count == 0)
+        return 0;
+    DeviceGuard guard(b->device_id);
+    // cudapoa_batch.cuh:171-178
+    GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(b->P.sequences), b->h_sequences, b->num_nucleotides_copied, cudaMemcpyHostToDevice, b->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<int8_t*>(b->P.weights), b->h_weights, b->num_nucleotides_copied, cudaMemcpyHostToDevice, b->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<WindowInfo*>(b->P.windows), b->h_windows, sizeof(WindowInfo) * b->poa_count, cudaMemcpyHostToDevice, b->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(b->P.seq_lengths), b->h_seq_lengths, sizeof(int32_t) * b->global_sequence_idx, cudaMemcpyHostToDevice, b->stream));
+    return 0;
+}
+
+int gwb200_poa_batch_launch(gwb200_poa_batch* b)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    if (b->poa_count == 0)
+        return 0;
+    DeviceGuard guard(b->device_id);
+    b->P.n_windows = b->poa_count;
+    GWB200_CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+    if (!b->score32 && !b->size32)
+        launch_typed<int16_t, int16_t>(b);
+    else if (b->score32 && !b->size32)
+        launch_typed<int32_t, int16_t>(b);
+    else
+        launch_typed<int32_t, int32_t>(b);
+    GWB200_CUDA_TRY(cudaPeekAtLastError());
+    GWB200_CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    b->launched        = true;
+    b->results_on_host = false;
+    return 0;
+}
+
+int gwb200_poa_batch_generate(gwb200_poa_batch* b)
+{
+    if (int rc = gwb200_poa_batch_upload(b))
+        return rc;
+    return gwb200_poa_batch_launch(b);
+}
+
+int gwb200_poa_batch_sync(gwb200_poa_batch* b)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    DeviceGuard guard(b->device_id);
+    GWB200_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+static int fetch_status(gwb200_poa_batch* b)
+{
+    const int64_t n = b->poa_count;
+    GWB200_CUDA_TRY(cudaMemcpyAsync(b->h_status, b->P.status, 4 * n, cudaMemcpyDeviceToHost, b->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(b->h_cons_len, b->P.consensus_len, 4 * n, cudaMemcpyDeviceToHost, b->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(b->h_node_count, b->P.node_count, 4 * n, cudaMemcpyDeviceToHost, b->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(b->h_cells, b->P.cells, 8 * n, cudaMemcpyDeviceToHost, b->stream));
+    return 0;
+}
+
+int gwb200_poa_batch_get_consensus(gwb200_poa_batch* b, char* consensus, uint16_t* coverage, int32_t* lengths, int32_t* status)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    if (!(b->output_mask & GWB200_POA_OUTPUT_CONSENSUS))
+        return GWB200_POA_OUTPUT_TYPE_UNAVAILABLE;
+    DeviceGuard guard(b->device_id);
+    const int64_t n  = b->poa_count;
+    const int64_t mc = b->cfg.max_consensus_size;
+    if (n == 0)
+        return GWB200_POA_SUCCESS;
+    if (!b->launched)
+        return set_error(GWB200_E_RUNTIME, "get_consensus called before generate_poa");
+    // unlike the reference (max_poas rows, cudapoa_batch.cuh:214-223) only the poa_count rows in use are copied
+    GWB200_CUDA_TRY(cudaMemcpyAsync(b->h_consensus, b->P.consensus, n * mc, cudaMemcpyDeviceToHost, b->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(b->h_coverage, b->P.coverage, n * mc * 2, cudaMemcpyDeviceToHost, b->stream));
+    if (int rc = fetch_status(b))
+        return rc;
+    GWB200_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->results_on_host = true;
+    for (int64_t w = 0; w < n; w++)
+    {
+        const int32_t st  = b->h_status[w];
+        const int32_t len = st == 0 ? b->h_cons_len[w] : 0;
+        if (status)
+            status[w] = st;
+        if (lengths)
+            lengths[w] = len;
+        if (consensus)
+        {
+            std::memcpy(consensus + w * mc, b->h_consensus + w * mc, len);
+            consensus[w * mc + len] = 0;
+        }
+        if (coverage)
+            std::memcpy(coverage + w * mc, b->h_coverage + w * mc, static_cast<size_t>(len) * 2);
+    }
+    return GWB200_POA_SUCCESS;
+}
+
+int gwb200_poa_batch_get_msa(gwb200_poa_batch* b, char* msa, int32_t* num_rows, int32_t* status)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    if (!(b->output_mask & GWB200_POA_OUTPUT_MSA))
+        return GWB200_POA_OUTPUT_TYPE_UNAVAILABLE;
+    DeviceGuard guard(b->device_id);
+    const int64_t n  = b->poa_count;
+    const int64_t mc = b->cfg.max_consensus_size;
+    const int64_t ms = b->cfg.max_sequences_per_poa;
+    if (n == 0)
+        return GWB200_POA_SUCCESS;
+    if (!b->launched)
+        return set_error(GWB200_E_RUNTIME, "get_msa called before generate_poa");
+    GWB200_CUDA_TRY(cudaMemcpyAsync(b->h_msa, b->P.msa_out, n * ms * mc, cudaMemcpyDeviceToHost, b->stream));
+    if (int rc = fetch_status(b))
+        return rc;
+    GWB200_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->results_on_host = true;
+    for (int64_t w = 0; w < n; w++)
+    {
+        const int32_t st = b->h_status[w];
+        if (status)
+            status[w] = st;
+        const int32_t rows = st == 0 ? b->h_windows[w].num_seqs : 0;
+        if (num_rows)
+            num_rows[w] = rows;
+        if (msa)
+        {
+            for (int32_t r = 0; r < rows; r++)
+            {
+                const char* src = reinterpret_cast<const char*>(b->h_msa + (w * ms + r) * mc);
+                char* dst       = msa + (w * ms + r) * mc;
+                const size_t l  = strnlen(src, mc - 1);
+                std::memcpy(dst, src, l);
+                dst[l] = 0;
+            }
+        }
+    }
+    return GWB200_POA_SUCCESS;
+}
+
+int gwb200_poa_batch_get_graphs(gwb200_poa_batch* b, int32_t* node_counts, int32_t* edge_counts, int32_t* status, uint8_t* node_labels,
+                                int32_t* edge_src, int32_t* edge_dst, int32_t* edge_weight)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    DeviceGuard guard(b->device_id);
+    const int64_t n  = b->poa_count;
+    const int64_t mn = b->cfg.max_nodes_per_graph;
+    if (n == 0)
+        return 0;
+    if (!b->launched)
+        return set_error(GWB200_E_RUNTIME, "get_graphs called before generate_poa");
+    if (int rc = fetch_status(b))
+        return rc;
+    std::vector<uint16_t> in_cnt(n * mn);
+    GWB200_CUDA_TRY(cudaMemcpyAsync(in_cnt.data(), b->P.in_cnt, n * mn * 2, cudaMemcpyDeviceToHost, b->stream));
+    GWB200_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    const bool fill = edge_src != nullptr;
+    std::vector<uint8_t> nodes, edges, wts;
+    if (fill)
+    {
+        nodes.resize(n * mn);
+        GWB200_CUDA_TRY(cudaMemcpy(nodes.data(), b->P.nodes, n * mn, cudaMemcpyDeviceToHost));
+    }
+    int64_t node_off = 0, edge_off = 0;
+    std::vector<uint8_t> ebuf(mn * b->size_bytes);
+    std::vector<uint16_t> wbuf(mn);
+    for (int64_t w = 0; w < n; w++)
+    {
+        const int32_t st = b->h_status[w];
+        if (status)
+            status[w] = st;
+        const int32_t nc = st == 0 ? b->h_node_count[w] : 0;
+        int32_t ec       = 0;
+        int32_t max_in   = 0;
+        for (int32_t i = 0; i < nc; i++)
+        {
+            ec += in_cnt[w * mn + i];
+            max_in = std::max<int32_t>(max_in, in_cnt[w * mn + i]);
+        }
+        if (node_counts)
+            node_counts[w] = nc;
+        if (edge_counts)
+            edge_counts[w] = ec;
+        if (fill && nc > 0)
+        {
+            std::memcpy(node_labels + node_off, nodes.data() + w * mn, nc);
+            // edges are emitted per sink node in slot order (cudapoa_batch.cuh:376-390); gather slot by slot
+            std::vector<int32_t> first(nc + 1, 0);
+            for (int32_t i = 0; i < nc; i++)
+                first[i + 1] = first[i] + in_cnt[w * mn + i];
+            for (int32_t slot = 0; slot < max_in; slot++)
+            {
+                const uint8_t* dsrc = static_cast<const uint8_t*>(b->P.in_edges) + (w * mn * kMaxEdges + slot * mn) * b->size_bytes;
+                GWB200_CUDA_TRY(cudaMemcpy(ebuf.data(), dsrc, nc * b->size_bytes, cudaMemcpyDeviceToHost));
+                GWB200_CUDA_TRY(cudaMemcpy(wbuf.data(), b->P.in_w + w * mn * kMaxEdges + slot * mn, nc * 2, cudaMemcpyDeviceToHost));
+                for (int32_t i = 0; i < nc; i++)
+                {
+                    if (slot < in_cnt[w * mn + i])
+                    {
+                        const int64_t k = edge_off + first[i] + slot;
+                        edge_src[k]     = b->size_bytes == 2 ? reinterpret_cast<int16_t*>(ebuf.data())[i] : reinterpret_cast<int32_t*>(ebuf.data())[i];
+                        edge_dst[k]     = i;
+                        edge_weight[k]  = wbuf[i];
+                    }
+                }
+            }
+        }
+        node_off += nc;
+        edge_off += ec;
+    }
+    return 0;
+}
+
+int64_t gwb200_poa_batch_last_cells(gwb200_poa_batch* b)
+{
+    if (!b || !b->launched)
+        return 0;
+    DeviceGuard guard(b->device_id);
+    if (!b->results_on_host)
+    {
+        if (fetch_status(b) != 0)
+            return -1;
+        cudaStreamSynchronize(b->stream);
+    }
+    int64_t tot = 0;
+    for (int32_t w = 0; w < b->poa_count; w++)
+        tot += static_cast<int64_t>(b->h_cells[w]);
+    return tot;
+}
+
+float gwb200_poa_batch_last_kernel_ms(gwb200_poa_batch* b)
+{
+    if (!b || !b->launched)
+        return 0.f;
+    DeviceGuard guard(b->device_id);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return -1.f;
+    }
+    return ms;
+}
+
+int gwb200_device_fdividef(int32_t n, const float* a, const float* b, float* out)
+{
+    if (n <= 0)
+        return 0;
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    GWB200_CUDA_TRY(cudaMalloc(&da, 4 * n));
+    GWB200_CUDA_TRY(cudaMalloc(&db, 4 * n));
+    GWB200_CUDA_TRY(cudaMalloc(&dout, 4 * n));
+    GWB200_CUDA_TRY(cudaMemcpy(da, a, 4 * n, cudaMemcpyHostToDevice));
+    GWB200_CUDA_TRY(cudaMemcpy(db, b, 4 * n, cudaMemcpyHostToDevice));
+    fdividef_kernel<<<(n + 255) / 256, 256>>>(n, da, db, dout);
+    count_launch();
+    GWB200_CUDA_TRY(cudaMemcpy(out, dout, 4 * n, cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return 0;
+}
+
+} // extern "C"

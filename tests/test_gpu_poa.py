@@ -1,0 +1,189 @@
+"""GPU parity tests for the POA path: the CUDA engine (through the C ABI) against
+  (1) the CPU oracle with the device's own fast-math division injected,
+  (2) the unmodified reference kernels (oracle/_ref/libgwref.so) run on the same GPU,
+  (3) the reference's end-to-end golden assembly (Test_CudapoaBatchEnd2End.cu:39-91).
+Bit-exact: consensus strings, coverage, MSA rows, status codes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import ref_lib
+from test_oracle_poa import GOLDEN, assembly, load_sample_windows  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg8(cfg):
+    return np.array([cfg.max_sequence_size, cfg.max_consensus_size, cfg.max_nodes_per_graph, cfg.matrix_sequence_dimension,
+                     cfg.alignment_band_width, cfg.max_sequences_per_poa, cfg.band_mode, cfg.max_banded_pred_distance], dtype=np.int32)
+
+
+@pytest.fixture(scope="module")
+def device_fdiv():
+    """Installs the device's __fdividef as the oracle's division (cudapoa_nw_banded.cuh:207 under -use_fast_math)."""
+    from genomeworks_b200 import cudapoa
+    cache = {}
+
+    def fdiv(a, b):
+        k = (a, b)
+        if k not in cache:
+            cache[k] = float(cudapoa.device_fdividef([a], [b])[0])
+        return cache[k]
+
+    cb = ol.FDIV_T(fdiv)
+    ol.lib().oracle_set_fdiv(C.cast(cb, C.c_void_p))
+    yield cb
+    ol.lib().oracle_set_fdiv(None)
+
+
+def run_ours(win_nseq, seq_len, data, cfg, msa=False, mem=8 << 30):
+    from genomeworks_b200 import cudapoa
+    batch = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, output_type="msa" if msa else "consensus", config=cfg)
+    rc, added = batch.add_poa_groups_flat(win_nseq, seq_len, data)
+    assert rc == 0 and added == len(win_nseq), (rc, added)
+    batch.generate_poa()
+    if msa:
+        rows, st = batch.get_msa()
+        out = dict(msa=[[r.decode() for r in w] for w in rows], status=np.array(st))
+    else:
+        cons, cov, st = batch.get_consensus()
+        out = dict(consensus=cons, coverage=cov, status=np.array(st))
+    out["cells"] = batch.last_cells()
+    out["kernel_ms"] = batch.last_kernel_ms()
+    batch.close()
+    return out
+
+
+def assert_same_consensus(a, b, what):
+    assert list(a["status"]) == list(b["status"]), what + ": status differs"
+    for w, (x, y) in enumerate(zip(a["consensus"], b["consensus"])):
+        assert x == y, "%s: consensus of window %d differs" % (what, w)
+    for w, (x, y) in enumerate(zip(a["coverage"], b["coverage"])):
+        assert list(x) == list(y), "%s: coverage of window %d differs" % (what, w)
+
+
+@pytest.mark.parametrize("band_mode", ["static_band", "adaptive_band", "full_band"])
+def test_small_windows_vs_oracle_and_reference(band_mode, device_fdiv):
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(48, 400, 12, 10, 5, 5, seed0=11)
+    cfg = cudapoa.make_config(1024, 16, 256, band_mode)
+    ours = run_ours(win_nseq, seq_len, data, cfg)
+    orc = ol.poa_run(synth.split_windows(win_nseq, seq_len, data), _cfg8(cfg))
+    assert_same_consensus(ours, orc, "oracle")
+    assert ours["cells"] == int(orc["cells"].sum())
+    if ref_lib.have_gwref():
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 256, cfg.band_mode)
+        assert_same_consensus(ours, ref, "reference")
+
+
+def test_c2_config_subset_vs_oracle_and_reference(device_fdiv):
+    """BASELINE config C2 (1 kb x 16 reads, static band 256, int16 scores) on 96 windows."""
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(96, 1000, 16, 20, 10, 10, seed0=1000, max_read_len=1024)
+    cfg = cudapoa.make_config(1024, 16, 256, "static_band")
+    ours = run_ours(win_nseq, seq_len, data, cfg)
+    assert (ours["status"] == 0).all()
+    orc = ol.poa_run(synth.split_windows(win_nseq, seq_len, data), _cfg8(cfg))
+    assert_same_consensus(ours, orc, "oracle")
+    if ref_lib.have_gwref():
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 256, 1)
+        assert_same_consensus(ours, ref, "reference")
+
+
+def test_c2_full_size_vs_reference():
+    """All 1024 windows of config C2 against the reference kernels (size-independent check: every output identical)."""
+    if not ref_lib.have_gwref():
+        pytest.skip("oracle/_ref/libgwref.so not built")
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(1024, 1000, 16, 20, 10, 10, seed0=1000, max_read_len=1024)
+    cfg = cudapoa.make_config(1024, 16, 256, "static_band")
+    ours = run_ours(win_nseq, seq_len, data, cfg, mem=16 << 30)
+    ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 256, 1)
+    assert_same_consensus(ours, ref, "reference")
+    assert (ours["status"] == 0).all()
+
+
+@pytest.mark.parametrize("factor", [2.0, 6.0])
+def test_c3_long_reads_adaptive_int32(factor, device_fdiv):
+    """BASELINE config C3 shape (10 kb x 32 reads would take the CPU oracle minutes; 10 kb x 6 reads, 3 windows):
+    adaptive band, int32 scores. factor 2.0 also pins exceeded_adaptive_banded_matrix_size statuses."""
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(3, 10000, 6, 200, 100, 100, seed0=1000, max_read_len=10240)
+    cfg = cudapoa.make_config(10240, 32, 256, "adaptive_band", adaptive_storage_factor=factor)
+    ours = run_ours(win_nseq, seq_len, data, cfg, mem=24 << 30)
+    orc = ol.poa_run(synth.split_windows(win_nseq, seq_len, data), _cfg8(cfg))
+    assert_same_consensus(ours, orc, "oracle")
+    if ref_lib.have_gwref():
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 10240, 32, 256, 2, adaptive_storage_factor=factor)
+        assert_same_consensus(ours, ref, "reference")
+
+
+@pytest.mark.parametrize("band_mode", ["static_band", "adaptive_band"])
+def test_msa_vs_oracle_and_reference(band_mode, device_fdiv):
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(24, 300, 10, 10, 5, 5, seed0=77)
+    cfg = cudapoa.make_config(1024, 16, 256, band_mode)
+    ours = run_ours(win_nseq, seq_len, data, cfg, msa=True)
+    windows = synth.split_windows(win_nseq, seq_len, data)
+    orc = ol.poa_run(windows, _cfg8(cfg), msa=True)
+    assert list(ours["status"]) == list(orc["status"])
+    assert ours["msa"] == orc["msa"]
+    for rows, reads in zip(ours["msa"], windows):
+        for row, rd in zip(rows, reads):
+            assert row.replace("-", "") == rd
+    if ref_lib.have_gwref():
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 256, cfg.band_mode, msa=True)
+        assert list(ours["status"]) == list(ref["status"])
+        assert ours["msa"] == ref["msa"]
+
+
+def test_end2end_golden_through_gpu():
+    """Test_CudapoaBatchEnd2End.cu:39-91 replayed through the CUDA engine: BatchConfig(1024, 200) = full_band."""
+    from genomeworks_b200 import cudapoa
+    windows = load_sample_windows()
+    win_nseq, seq_len, data = ol.flatten_windows(windows)
+    cfg = cudapoa.make_config(1024, 200)
+    ours = run_ours(win_nseq, seq_len, data, cfg, mem=8 << 30)
+    assert (ours["status"] == 0).all()
+    golden = open(GOLDEN + "/sample-golden-value.txt").read().strip()
+    assert assembly(ours["consensus"], ours["coverage"]) == golden
+
+
+def test_batch_api_contracts():
+    """Test_CudapoaBatch.cu:70-203 + pygenomeworks/test/test_cudapoa_bindings.py."""
+    from genomeworks_b200 import cudapoa
+    # zero memory => runtime_error
+    with pytest.raises(RuntimeError):
+        cudapoa.CudaPoaBatch(10, 1024, 0, config=cudapoa.make_config(1024, 10))
+    with pytest.raises(ValueError):
+        cudapoa.CudaPoaBatch(10, 1024, -2, config=cudapoa.make_config(1024, 10))
+    b = cudapoa.CudaPoaBatch(10, 1024, 1 << 30, config=cudapoa.make_config(1024, 10, 256, "static_band"))
+    # 11th read => exceeded_maximum_sequences_per_poa on that entry only
+    st, per = b.add_poa_group(["ACGT" * 10] * 11)
+    assert st == cudapoa.success
+    assert per == [0] * 10 + [cudapoa.exceeded_maximum_sequences_per_poa]
+    # 1025-base read => exceeded_maximum_sequence_size on that entry
+    st, per = b.add_poa_group(["A" * 1025, "ACGT"])
+    assert st == cudapoa.success and per == [cudapoa.exceeded_maximum_sequence_size, 0]
+    st, per = b.add_poa_group(["A" * 1025])
+    assert st == cudapoa.empty_poa_group
+    assert b.total_poas == 3
+    b.reset()
+    assert b.total_poas == 0
+    seq = "A" * 1023
+    b.add_poa_group([seq, seq, seq])
+    b.generate_poa()
+    cons, cov, st = b.get_consensus()
+    assert st == [0] and cons == [seq] and cov[0] == [3] * 1023
+    with pytest.raises(RuntimeError):
+        b.get_msa()
+    # graph of 3 reads: 10 nodes / 11 edges (test_cudapoa_bindings.py)
+    b.reset()
+    b.add_poa_group(["ACTGACTG", "ACTTACTG", "ACTCACTG"])
+    b.generate_poa()
+    graphs, st = b.get_graphs()
+    assert st == [0]
+    assert graphs[0].number_of_nodes() == 10 and graphs[0].number_of_edges() == 11
+    b.close()
