@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract.
+
+Metric (BASELINE.json): POA consensus windows/sec on synthetic 10 kb x 32-read windows (config C3: adaptive band 256,
+int32 scores; adaptive_storage_factor 6.0 because 2.0 yields exceeded_adaptive_banded_matrix_size for every window on
+both this engine and the reference, SURVEY.md fact 3 / DESIGN.md). One "step" = one pass of the hot path over one batch
+of `--windows` windows per GPU. Windows shard embarrassingly: every rank owns a Batch and its own windows (weak scaling),
+NCCL is used only for the barrier / max-over-ranks timing and the result gather after the timed region.
+
+  value : windows/s, inputs packed and resident in HBM before the timed region (K x [launch, sync], CUDA events on the
+          batch stream, max over ranks)
+  e2e   : windows/s through the public API with HOST buffers every step: add_poa_group packing, H2D, kernel, D2H of
+          consensus + coverage (wall clock around barrier + synchronize, max over ranks)
+  roofline: algorithmic bytes = executed DP cells x sizeof(ScoreT) / kernel time, vs MEASURED_PEAKS hbm_gbs
+  cpu_baseline / --impl reference: 3rdparty/spoa (oracle/_ref/libspoa_ref.so, unmodified) on the host cores.
+
+Other workloads for development: --workload c2 (1 kb x 16, static band, 1024 windows), c4 (aligner 10k x 10k, bw 1024).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def workload_params(name, windows):
+    if name == "c3":
+        return dict(kind="poa", name="C3: cudapoa long-read consensus, 10 kb x 32 reads/window, adaptive band 256, int32 scores, "
+                    "adaptive_storage_factor 6.0", backbone=10000, reads=32, mut=200, ins=100, dele=100, max_seq=10240, band=256,
+                    band_mode="adaptive_band", factor=6.0, windows=windows or 296)
+    if name == "c2":
+        return dict(kind="poa", name="C2: cudapoa short-read consensus, 1 kb x 16 reads/window, static band 256, int16 scores",
+                    backbone=1000, reads=16, mut=20, ins=10, dele=10, max_seq=1024, band=256, band_mode="static_band", factor=2.0,
+                    windows=windows or 1024)
+    if name == "c4":
+        return dict(kind="aligner", name="C4: cudaaligner global, 10000 x 10000 bp, Myers banded (max_bandwidth 1024)", genome=10000,
+                    max_bw=1024, windows=windows or 512)
+    raise SystemExit("unknown workload " + name)
+
+
+def spoa_sample(wp, n_windows, seed0, threads=0):
+    import ref_lib
+    from genomeworks_b200 import synth
+    win_nseq, seq_len, data = synth.poa_windows(n_windows, wp["backbone"], wp["reads"], wp["mut"], wp["ins"], wp["dele"], seed0=seed0,
+                                                max_read_len=wp["max_seq"])
+    r = ref_lib.spoa_consensus(win_nseq, seq_len, data, n_threads=threads, want_strings=False)
+    return r
+
+
+def run_reference_arm(args, wp, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (3rdparty/spoa, unmodified, oracle/_ref) on
+    the box's host cores. Rank 0 only."""
+    if rank != 0:
+        return
+    import ref_lib
+    if wp["kind"] != "poa":
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU reference implementation is named for the aligner path"}))
+        return
+    if not ref_lib.have_spoa():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libspoa_ref.so is not built"}))
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: one window per host thread per step (10 kb x 32 reads is ~3.1e9 spoa DP cells per window)
+    per_step = max(1, min(cores, 256)) if wp["backbone"] >= 5000 else max(8, 8 * cores)
+    times, cells = [], 0.0
+    for it in range(args.warmup + args.steps):
+        r = spoa_sample(wp, per_step, 1000 + it * per_step, threads=cores)
+        if it >= args.warmup:
+            times.append(r["seconds"])
+            cells += r["cells"]
+    total = sum(times)
+    value = per_step * len(times) / total
+    line = {
+        "impl": "reference", "metric": "poa_consensus_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16 (spoa AVX2 SIMD)", "data": "synthetic",
+        "config": {"workload": wp["name"], "windows_per_step": per_step, "engine": "3rdparty/spoa kNW linear gaps, full DP, all host threads"},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "reference",
+                         "sample": "%d windows per step x %d steps, spoa DP cells/s %.3e" % (per_step, len(times), cells / total)},
+        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
+    ap.add_argument("--windows", type=int, default=0, help="windows (or pairs) per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-reference", action="store_true", help="also time the reference CUDA kernels (oracle/_ref) on rank 0")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wp = workload_params(args.workload, args.windows)
+
+    if args.impl == "reference":
+        run_reference_arm(args, wp, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    from genomeworks_b200 import _lib
+    L = _lib.lib()
+    if wp["kind"] == "aligner":
+        from bench_aligner import run_aligner_bench
+        run_aligner_bench(args, wp, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    from genomeworks_b200 import cudapoa, synth
+    n_win = wp["windows"]
+    # every rank owns its own windows (seeds disjoint across ranks): weak scaling, no data-path collective
+    win_nseq, seq_len, data = synth.poa_windows(n_win, wp["backbone"], wp["reads"], wp["mut"], wp["ins"], wp["dele"],
+                                                seed0=1000 + rank * n_win, max_read_len=wp["max_seq"])
+    cfg = cudapoa.make_config(wp["max_seq"], wp["reads"], wp["band"], wp["band_mode"], adaptive_storage_factor=wp["factor"])
+    stream = torch.cuda.Stream()
+    free_b, _ = torch.cuda.mem_get_info()
+    batch = cudapoa.CudaPoaBatch(wp["reads"], wp["max_seq"], int(free_b * 0.92), config=cfg, device_id=local_rank, stream=stream)
+    if batch.max_poas < n_win:
+        raise SystemExit("batch capacity %d < requested windows %d" % (batch.max_poas, n_win))
+
+    launches0 = L.gwb200_kernel_launch_count()
+
+    # ---------------- device-resident timing (`value`) ----------------
+    rc, added = batch.add_poa_groups_flat(win_nseq, seq_len, data)
+    assert rc == 0 and added == n_win
+    batch.upload()
+    batch.sync()
+    for _ in range(args.warmup):
+        batch.launch()
+        batch.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    launches_before_timed = L.gwb200_kernel_launch_count()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            batch.launch()
+        ev1.record(stream)
+    stream.synchronize()
+    barrier()
+    timed_launches = L.gwb200_kernel_launch_count() - launches_before_timed
+    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = max_over_ranks(dev_ms)
+    clocks = sampler.stop() if rank == 0 else None
+    cells = batch.last_cells()
+    last_kernel_ms = batch.last_kernel_ms()
+    c, cov, lens, st = batch.get_consensus_arrays()
+    n_ok = int((st == 0).sum())
+    total_windows = sum_over_ranks(float(n_win))
+    value = total_windows * args.steps / (dev_ms / 1e3)
+
+    # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
+    h2d = int(((seq_len + 3) // 4 * 4).sum()) * 2 + 24 * n_win + 4 * len(seq_len)
+    d2h = n_win * cfg.max_consensus_size * 3 + n_win * 20
+    for _ in range(max(1, min(args.warmup, 2))):
+        batch.reset()
+        batch.add_poa_groups_flat(win_nseq, seq_len, data)
+        batch.generate_poa()
+        batch.get_consensus_arrays()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.reset()
+        batch.add_poa_groups_flat(win_nseq, seq_len, data)
+        batch.generate_poa()
+        c2, cov2, lens2, st2 = batch.get_consensus_arrays()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = total_windows * args.steps / e2e_s
+    assert (lens2 == lens).all() and (st2 == st).all()
+
+    # result gather over NCCL (outside the timed regions): per-window status + consensus length to rank 0
+    if world > 1:
+        mine = torch.from_numpy(np.stack([st.astype(np.int32), lens.astype(np.int32)], 1)).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+        if rank == 0:
+            n_ok = int(sum(int((g[:, 0] == 0).sum().item()) for g in gathered))
+
+    launches = L.gwb200_kernel_launch_count() - launches0
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        sb = batch.score_bytes
+        k_ms = dev_ms / args.steps
+        achieved = cells * sb / (k_ms / 1e3) / 1e9
+        line = {
+            "metric": "poa_consensus_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32" if sb == 4 else "int16", "data": "synthetic",
+            "config": {"workload": wp["name"], "windows_per_gpu_per_step": n_win, "reads_per_window": wp["reads"],
+                       "band_mode": wp["band_mode"], "band_width": wp["band"], "scores": "gap -8 mismatch -6 match 8",
+                       "parallelism": "windows sharded over %d GPU(s), one Batch per rank" % world,
+                       "l2": "score matrices written per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (cells * sb / 1e9),
+                       "windows_ok_last_step": n_ok},
+            "dp_cells_per_step_per_gpu": cells, "dp_cells_per_s": cells * world / (k_ms / 1e3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "poa_window_kernel", "algorithmic_bytes_per_cell": sb,
+                         "kernel_ms_per_launch": k_ms},
+            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(timed_launches), "gpu_launches_total": int(launches), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            try:
+                import ref_lib
+                if ref_lib.have_spoa():
+                    cores = os.cpu_count() or 1
+                    ns = max(1, min(cores, 256)) if wp["backbone"] >= 5000 else 8 * cores
+                    r = spoa_sample(wp, ns, 1000, threads=cores)
+                    line["cpu_baseline"] = {"value": ns / r["seconds"], "unit": "windows/s", "cores": cores, "kind": "reference",
+                                            "sample": "%d windows of the same workload, unmodified 3rdparty/spoa (AVX2), %.1f s, %.3e DP cells/s"
+                                                      % (ns, r["seconds"], r["cells"] / r["seconds"])}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": 0, "kind": "reference",
+                                            "sample": "oracle/_ref/libspoa_ref.so not built"}
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+        if args.gpu_reference:
+            try:
+                import ref_lib
+                if ref_lib.have_gwref():
+                    batch.close()
+                    bm = {"full_band": 0, "static_band": 1, "adaptive_band": 2}[wp["band_mode"]]
+                    rr = ref_lib.ref_poa_run(win_nseq, seq_len, data, wp["max_seq"], wp["reads"], wp["band"], bm,
+                                             adaptive_storage_factor=wp["factor"], mem_fraction=0.9, max_windows_per_batch=n_win)
+                    rr = ref_lib.ref_poa_run(win_nseq, seq_len, data, wp["max_seq"], wp["reads"], wp["band"], bm,
+                                             adaptive_storage_factor=wp["factor"], mem_fraction=0.9, max_windows_per_batch=n_win)
+                    same = all(bytes(c[i, :lens[i]]).decode() == rr["consensus"][i] for i in range(n_win)) and list(rr["status"]) == list(st)
+                    line["gpu_reference"] = {"value": n_win / (rr["timings"][1] / 1e3), "unit": "windows/s",
+                                             "what": "unmodified reference cudapoa rebuilt for sm_100a, generate_poa+get_consensus wall time, "
+                                                     "same windows, same GPU", "batches": int(rr["timings"][2]), "identical_outputs": bool(same)}
+            except Exception as e:  # pragma: no cover
+                line["gpu_reference"] = {"value": None, "what": "failed: %r" % (e,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
