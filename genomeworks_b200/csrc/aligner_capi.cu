@@ -1,0 +1,527 @@
+// gw-b200: host engine + C ABI for the banded Myers global aligner (include/gwb200.h names the reference interface each
+// entry replaces). Host behaviour follows cudaaligner/src/aligner_global_myers_banded.cpp (bandwidth clamp, admission,
+// scheduling by size, result decoding); memory layout and kernels are this repo's own (myers_kernels.cuh).
+// No CPU fallback.
+
+#include "../../include/gwb200.h"
+#include "common.cuh"
+#include "myers_kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace gwb200;
+using namespace gwb200::myers;
+
+namespace
+{
+
+constexpr int32_t kBlocksPerSM = 8;
+
+// compute_matrix_size_for_alignment, aligner_global_myers_banded.cpp:47-55
+int64_t matrix_size_for_alignment(int32_t query_size, int32_t target_size, int32_t max_bandwidth)
+{
+    const int32_t p            = (max_bandwidth + 1) / 2;
+    const int32_t bandwidth    = std::min(1 + 2 * p, query_size);
+    const int64_t n_words_band = (bandwidth + 31) / 32;
+    return n_words_band * (static_cast<int64_t>(target_size) + 1);
+}
+
+template <typename T>
+struct DevBuf
+{
+    T* p       = nullptr;
+    int64_t n  = 0;
+    bool ensure(int64_t count)
+    {
+        if (count <= n)
+            return true;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+        int64_t want = count + count / 8 + 64;
+        if (cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return false;
+        }
+        n = want;
+        return true;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <typename T>
+struct PinBuf
+{
+    T* p      = nullptr;
+    int64_t n = 0;
+    bool ensure(int64_t count, bool keep)
+    {
+        if (count <= n)
+            return true;
+        int64_t want = count + count / 4 + 64;
+        T* q         = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&q), want * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return false;
+        }
+        if (p)
+        {
+            if (keep)
+                std::memcpy(q, p, n * sizeof(T));
+            cudaFreeHost(p);
+        }
+        p = q;
+        n = want;
+        return true;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct AlnResult
+{
+    int32_t status     = GWB200_ALN_UNINITIALIZED;
+    int32_t is_optimal = 0;
+    std::vector<int8_t> actions;
+    std::vector<int32_t> runs;
+};
+
+} // namespace
+
+struct gwb200_aligner
+{
+    int32_t device_id = 0;
+    cudaStream_t stream = nullptr;
+    int32_t max_bandwidth = 0;
+    int64_t max_device_memory = 0;
+    int32_t n_sms = 0;
+
+    // host inputs
+    PinBuf<char> seq_h;
+    std::vector<int64_t> seq_starts_h{0};
+    std::vector<int32_t> max_bw_h;
+    int64_t max_matrix = 0;
+    int32_t max_query  = 0;
+
+    // device
+    DevBuf<char> seq_d;
+    DevBuf<int64_t> seq_starts_d;
+    DevBuf<int32_t> max_bw_d, sched_d, counter_d, path_len_d, offsets_d, slot_runs_d, runs_d;
+    DevBuf<uint32_t> metadata_d;
+    DevBuf<int8_t> slot_actions_d, actions_d;
+    DevBuf<WordType> pv_d, mv_d, qpat_d;
+    DevBuf<int32_t> score_d;
+    DevBuf<unsigned long long> cells_d;
+
+    // pinned outputs
+    PinBuf<int32_t> offsets_h, runs_h;
+    PinBuf<uint32_t> metadata_h;
+    PinBuf<int8_t> actions_h;
+    PinBuf<unsigned long long> cells_h;
+
+    std::vector<AlnResult> results;
+    int32_t n_launched = 0;
+    bool aligned       = false;
+    bool synced        = false;
+    int64_t total_len  = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int32_t num_alignments() const { return static_cast<int32_t>(seq_starts_h.size() / 2); }
+};
+
+namespace
+{
+
+int64_t memory_requirement(const gwb200_aligner* a, int64_t max_matrix, int32_t max_query, int64_t seq_sum, int32_t n)
+{
+    // same accounting shape as fits_device_memory (aligner_global_myers_banded.cpp:494-538): workspaces for every resident
+    // CTA + sequences, result slots and per-alignment arrays
+    const int64_t n_blocks = std::min<int64_t>(static_cast<int64_t>(a->n_sms) * kBlocksPerSM, std::max(n, 1));
+    const int64_t qpat     = 4ll * ((max_query + 31) / 32);
+    int64_t req            = n_blocks * (max_matrix * 12 + qpat * 4);
+    req += seq_sum * (1 + 1 + 4 + 1 + 4); // sequences, slots (actions + runs), compacted (actions + runs)
+    req += (2ll * n + 1) * 8 + n * (4 + 4 + 4 + 4 + 4) + 4096 * 16;
+    return req;
+}
+
+} // namespace
+
+extern "C" {
+
+int gwb200_aligner_init(void) { return GWB200_ALN_SUCCESS; }
+
+int gwb200_aligner_reset_max_bandwidth(gwb200_aligner* a, int32_t max_bandwidth)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    if (max_bandwidth < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_bandwidth cannot be negative.");
+    if (max_bandwidth % 32 == 1)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "Invalid max_bandwidth. max_bandwidth % 32 == 1 is not allowed. Please change it by +/-1.");
+    gwb200_aligner_reset(a);
+    a->max_bandwidth = max_bandwidth;
+    return 0;
+}
+
+int gwb200_aligner_create(gwb200_aligner** out, int32_t max_bandwidth, void* stream, int32_t device_id, int64_t max_device_memory)
+{
+    if (!out)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (max_device_memory < -1)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_device_memory has to be either -1 (=all available GPU memory) or greater or equal than 0.");
+    if (max_bandwidth < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_bandwidth cannot be negative.");
+    if (max_bandwidth % 32 == 1)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "Invalid max_bandwidth. max_bandwidth % 32 == 1 is not allowed. Please change it by +/-1.");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_id < 0 || ndev <= device_id)
+    {
+        cudaGetLastError();
+        return set_error(GWB200_E_CUDA, "no usable CUDA device: this engine has no CPU fallback");
+    }
+    DeviceGuard guard(device_id);
+    gwb200_aligner* a = new gwb200_aligner;
+    a->device_id      = device_id;
+    a->stream         = static_cast<cudaStream_t>(stream);
+    a->max_bandwidth  = max_bandwidth;
+    cudaDeviceGetAttribute(&a->n_sms, cudaDevAttrMultiProcessorCount, device_id);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    a->max_device_memory = max_device_memory < 0 ? static_cast<int64_t>(free_b * 0.95) : max_device_memory;
+    cudaEventCreate(&a->ev0);
+    cudaEventCreate(&a->ev1);
+    *out = a;
+    return 0;
+}
+
+void gwb200_aligner_destroy(gwb200_aligner* a)
+{
+    if (!a)
+        return;
+    DeviceGuard guard(a->device_id);
+    cudaStreamSynchronize(a->stream);
+    a->seq_h.release();
+    a->seq_d.release();
+    a->seq_starts_d.release();
+    a->max_bw_d.release();
+    a->sched_d.release();
+    a->counter_d.release();
+    a->path_len_d.release();
+    a->offsets_d.release();
+    a->slot_runs_d.release();
+    a->runs_d.release();
+    a->metadata_d.release();
+    a->slot_actions_d.release();
+    a->actions_d.release();
+    a->pv_d.release();
+    a->mv_d.release();
+    a->qpat_d.release();
+    a->score_d.release();
+    a->cells_d.release();
+    a->offsets_h.release();
+    a->runs_h.release();
+    a->metadata_h.release();
+    a->actions_h.release();
+    a->cells_h.release();
+    if (a->ev0)
+        cudaEventDestroy(a->ev0);
+    if (a->ev1)
+        cudaEventDestroy(a->ev1);
+    delete a;
+}
+
+// aligner_global_myers_banded.cpp:155-258
+int gwb200_aligner_add_alignment(gwb200_aligner* a, int32_t max_bandwidth, const char* query, int32_t query_length, const char* target,
+                                 int32_t target_length, int32_t reverse_complement_query, int32_t reverse_complement_target)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    if (max_bandwidth <= 0)
+        max_bandwidth = a->max_bandwidth;
+    if (max_bandwidth < 0 || query_length < 0 || target_length < 0 || query == nullptr || target == nullptr)
+        return GWB200_ALN_GENERIC_ERROR;
+    const int32_t n = a->num_alignments();
+    if (max_bandwidth > query_length)
+        max_bandwidth = (query_length % 32 == 1 ? query_length + 1 : query_length); // guarantees max_bandwidth % 32 != 1 on the device
+    const int64_t matrix = matrix_size_for_alignment(query_length, target_length, max_bandwidth);
+    const int64_t new_max_matrix = std::max(a->max_matrix, matrix);
+    const int32_t new_max_query  = std::max(a->max_query, query_length);
+    const int64_t new_sum        = a->seq_starts_h.back() + query_length + target_length;
+    if (((static_cast<uint32_t>(n + 1)) & ~((1u << 27) - 1)) != 0u || new_sum > static_cast<int64_t>(INT32_MAX) ||
+        memory_requirement(a, new_max_matrix, new_max_query, new_sum, n + 1) >= a->max_device_memory)
+    {
+        if (n == 0)
+            return set_error(GWB200_E_RUNTIME, "Could not fit alignment into device or host memory.");
+        return GWB200_ALN_EXCEEDED_MAX_ALIGNMENTS;
+    }
+    if (!a->seq_h.ensure(new_sum + 16, true))
+        return GWB200_ALN_EXCEEDED_MAX_ALIGNMENTS;
+    char* dst = a->seq_h.p + a->seq_starts_h.back();
+    auto copy = [](const char* src, int32_t len, char* d, bool rc) {
+        if (!rc)
+        {
+            std::memcpy(d, src, len);
+            return;
+        }
+        static const char lookup[4] = {'T', 'G', 'A', 'C'};
+        for (int32_t pos = 0; pos < len; ++pos)
+            d[pos] = lookup[(static_cast<unsigned char>(src[len - 1 - pos]) >> 1) & 0x3];
+    };
+    copy(query, query_length, dst, reverse_complement_query != 0);
+    copy(target, target_length, dst + query_length, reverse_complement_target != 0);
+    a->seq_starts_h.push_back(a->seq_starts_h.back() + query_length);
+    a->seq_starts_h.push_back(a->seq_starts_h.back() + target_length);
+    a->max_bw_h.push_back(max_bandwidth);
+    a->max_matrix = new_max_matrix;
+    a->max_query  = new_max_query;
+    a->aligned    = false;
+    a->synced     = false;
+    return GWB200_ALN_SUCCESS;
+}
+
+int32_t gwb200_aligner_num_alignments(const gwb200_aligner* a) { return a ? a->num_alignments() : 0; }
+
+// aligner_global_myers_banded.cpp:260-374
+int gwb200_aligner_align_all(gwb200_aligner* a)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    const int32_t n = a->num_alignments();
+    if (n == 0)
+        return GWB200_ALN_SUCCESS;
+    DeviceGuard guard(a->device_id);
+    const int64_t seq_sum  = a->seq_starts_h.back();
+    const int32_t n_blocks = static_cast<int32_t>(std::min<int64_t>(static_cast<int64_t>(a->n_sms) * kBlocksPerSM, n));
+    const int32_t qpat_el  = 4 * ((a->max_query + 31) / 32) + 4;
+    const int64_t ws       = std::max<int64_t>(a->max_matrix, 1);
+    bool ok = a->seq_d.ensure(seq_sum + 16) && a->seq_starts_d.ensure(2ll * n + 1) && a->max_bw_d.ensure(n) && a->sched_d.ensure(n) &&
+              a->counter_d.ensure(1) && a->path_len_d.ensure(n) && a->offsets_d.ensure(n + 1) && a->metadata_d.ensure(n) &&
+              a->slot_actions_d.ensure(seq_sum + 16) && a->slot_runs_d.ensure(seq_sum + 16) && a->actions_d.ensure(seq_sum + 16) &&
+              a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(ws * n_blocks) && a->mv_d.ensure(ws * n_blocks) &&
+              a->score_d.ensure(ws * n_blocks) && a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
+              a->offsets_h.ensure(n + 1, false) && a->metadata_h.ensure(n, false) && a->cells_h.ensure(1, false);
+    if (!ok)
+        return set_error(GWB200_E_RUNTIME, "Out of memory.");
+
+    // scheduling index: largest alignments first (:306-309)
+    std::vector<int32_t> sched(n);
+    std::iota(sched.begin(), sched.end(), 0);
+    const std::vector<int64_t>& st = a->seq_starts_h;
+    std::stable_sort(sched.begin(), sched.end(), [&st](int32_t i, int32_t j) { return st[2 * i + 2] - st[2 * i] > st[2 * j + 2] - st[2 * j]; });
+
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->seq_d.p, a->seq_h.p, seq_sum, cudaMemcpyHostToDevice, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->seq_starts_d.p, st.data(), (2ll * n + 1) * 8, cudaMemcpyHostToDevice, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->max_bw_d.p, a->max_bw_h.data(), 4ll * n, cudaMemcpyHostToDevice, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->sched_d.p, sched.data(), 4ll * n, cudaMemcpyHostToDevice, a->stream));
+    GWB200_CUDA_TRY(cudaMemsetAsync(a->counter_d.p, 0, 4, a->stream));
+    GWB200_CUDA_TRY(cudaMemsetAsync(a->cells_d.p, 0, 8, a->stream));
+    // the host vectors above are pageable: make sure the copies have consumed them before they go out of scope
+    GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+
+    DeviceParams P{};
+    P.seqs          = a->seq_d.p;
+    P.seq_starts    = a->seq_starts_d.p;
+    P.max_bw        = a->max_bw_d.p;
+    P.sched_index   = a->sched_d.p;
+    P.sched_counter = a->counter_d.p;
+    P.n_alignments  = n;
+    P.pv            = a->pv_d.p;
+    P.mv            = a->mv_d.p;
+    P.score         = a->score_d.p;
+    P.ws_elems      = ws;
+    P.qpat          = a->qpat_d.p;
+    P.qpat_elems    = qpat_el;
+    P.slot_actions  = a->slot_actions_d.p;
+    P.slot_runs     = a->slot_runs_d.p;
+    P.path_len      = a->path_len_d.p;
+    P.metadata      = a->metadata_d.p;
+    P.cells         = a->cells_d.p;
+
+    GWB200_CUDA_TRY(cudaEventRecord(a->ev0, a->stream));
+    myers_banded_kernel<<<n_blocks, 32, 0, a->stream>>>(P);
+    offsets_kernel<<<1, 1024, 0, a->stream>>>(a->path_len_d.p, n, a->offsets_d.p);
+    compact_kernel<<<(n * 32 + 255) / 256, 256, 0, a->stream>>>(P, a->offsets_d.p, a->actions_d.p, a->runs_d.p);
+    count_launch(3);
+    GWB200_CUDA_TRY(cudaPeekAtLastError());
+    GWB200_CUDA_TRY(cudaEventRecord(a->ev1, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->offsets_h.p, a->offsets_d.p, 4ll * (n + 1), cudaMemcpyDeviceToHost, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->metadata_h.p, a->metadata_d.p, 4ll * n, cudaMemcpyDeviceToHost, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->cells_h.p, a->cells_d.p, 8, cudaMemcpyDeviceToHost, a->stream));
+    a->n_launched = n;
+    a->aligned    = true;
+    a->synced     = false;
+    return GWB200_ALN_SUCCESS;
+}
+
+// aligner_global_myers_banded.cpp:376-430
+int gwb200_aligner_sync_alignments(gwb200_aligner* a)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    DeviceGuard guard(a->device_id);
+    const int32_t n = a->num_alignments();
+    a->results.clear();
+    a->results.resize(n);
+    if (n == 0 || !a->aligned)
+    {
+        GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+        return GWB200_ALN_SUCCESS;
+    }
+    GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream)); // offsets + metadata are on the host now
+    const int64_t total = a->offsets_h.p[n];
+    a->total_len        = total;
+    if (!a->actions_h.ensure(total + 16, false) || !a->runs_h.ensure(total + 16, false))
+        return set_error(GWB200_E_RUNTIME, "Out of memory.");
+    if (total > 0)
+    {
+        GWB200_CUDA_TRY(cudaMemcpyAsync(a->actions_h.p, a->actions_d.p, total, cudaMemcpyDeviceToHost, a->stream));
+        GWB200_CUDA_TRY(cudaMemcpyAsync(a->runs_h.p, a->runs_d.p, total * 4, cudaMemcpyDeviceToHost, a->stream));
+        GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+    }
+    for (int32_t i = 0; i < n; ++i)
+    {
+        const uint32_t md   = a->metadata_h.p[i];
+        const int32_t index = static_cast<int32_t>(md & ((1u << 27) - 1));
+        const bool optimal  = (md >> 31) != 0;
+        const int64_t b     = a->offsets_h.p[i];
+        const int64_t e     = a->offsets_h.p[i + 1];
+        const int32_t ql    = static_cast<int32_t>(a->seq_starts_h[2 * index + 1] - a->seq_starts_h[2 * index]);
+        const int32_t tl    = static_cast<int32_t>(a->seq_starts_h[2 * index + 2] - a->seq_starts_h[2 * index + 1]);
+        AlnResult& r        = a->results[index];
+        if (b != e || (ql == 0 && tl == 0))
+        {
+            // the device path runs end -> start; the host reverses it (:423)
+            r.actions.assign(std::make_reverse_iterator(a->actions_h.p + e), std::make_reverse_iterator(a->actions_h.p + b));
+            r.runs.assign(std::make_reverse_iterator(a->runs_h.p + e), std::make_reverse_iterator(a->runs_h.p + b));
+            r.is_optimal = optimal ? 1 : 0;
+            r.status     = GWB200_ALN_SUCCESS;
+        }
+    }
+    a->synced = true;
+    // like the reference, the inputs are consumed by sync_alignments (reset_data(), :428)
+    a->seq_starts_h.assign(1, 0);
+    a->max_bw_h.clear();
+    a->max_matrix = 0;
+    a->max_query  = 0;
+    a->aligned    = false;
+    return GWB200_ALN_SUCCESS;
+}
+
+int gwb200_aligner_result_info(const gwb200_aligner* a, int32_t i, int32_t* status, int32_t* is_optimal, int32_t* n_runs)
+{
+    if (!a || i < 0 || i >= static_cast<int32_t>(a->results.size()))
+        return set_error(GWB200_E_INVALID_ARGUMENT, "alignment index out of range");
+    const AlnResult& r = a->results[i];
+    if (status)
+        *status = r.status;
+    if (is_optimal)
+        *is_optimal = r.is_optimal;
+    if (n_runs)
+        *n_runs = static_cast<int32_t>(r.actions.size());
+    return 0;
+}
+
+int gwb200_aligner_result_runs(const gwb200_aligner* a, int32_t i, int8_t* actions, int32_t* runlengths)
+{
+    if (!a || i < 0 || i >= static_cast<int32_t>(a->results.size()))
+        return set_error(GWB200_E_INVALID_ARGUMENT, "alignment index out of range");
+    const AlnResult& r = a->results[i];
+    if (actions && !r.actions.empty())
+        std::memcpy(actions, r.actions.data(), r.actions.size());
+    if (runlengths && !r.runs.empty())
+        std::memcpy(runlengths, r.runs.data(), r.runs.size() * 4);
+    return 0;
+}
+
+int gwb200_aligner_reset(gwb200_aligner* a)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    a->seq_starts_h.assign(1, 0);
+    a->max_bw_h.clear();
+    a->max_matrix = 0;
+    a->max_query  = 0;
+    a->results.clear();
+    a->aligned = false;
+    a->synced  = false;
+    return 0;
+}
+
+int gwb200_aligner_free_temporary_device_buffers(gwb200_aligner* a)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    DeviceGuard guard(a->device_id);
+    cudaStreamSynchronize(a->stream);
+    a->pv_d.release();
+    a->mv_d.release();
+    a->score_d.release();
+    a->qpat_d.release();
+    a->slot_actions_d.release();
+    a->slot_runs_d.release();
+    return 0;
+}
+
+int gwb200_aligner_get_alignments_device(const gwb200_aligner* a, const int8_t** cigar_operations, const int32_t** cigar_runlengths,
+                                         const int32_t** cigar_offsets, const uint32_t** metadata, int64_t* total_length, int32_t* n_alignments)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    if (cigar_operations)
+        *cigar_operations = a->actions_d.p;
+    if (cigar_runlengths)
+        *cigar_runlengths = a->runs_d.p;
+    if (cigar_offsets)
+        *cigar_offsets = a->offsets_d.p;
+    if (metadata)
+        *metadata = a->metadata_d.p;
+    if (total_length)
+        *total_length = a->total_len;
+    if (n_alignments)
+        *n_alignments = a->n_launched;
+    return 0;
+}
+
+int64_t gwb200_aligner_last_cells(gwb200_aligner* a)
+{
+    if (!a || !a->cells_h.p)
+        return 0;
+    DeviceGuard guard(a->device_id);
+    cudaStreamSynchronize(a->stream);
+    return static_cast<int64_t>(a->cells_h.p[0]);
+}
+
+float gwb200_aligner_last_kernel_ms(gwb200_aligner* a)
+{
+    if (!a)
+        return 0.f;
+    DeviceGuard guard(a->device_id);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a->ev0, a->ev1) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return -1.f;
+    }
+    return ms;
+}
+
+} // extern "C"

@@ -1,0 +1,794 @@
+// gw-b200 banded Myers / Ukkonen global aligner, device code (sm_100a). One alignment per warp, persistent CTAs.
+//
+// Behavioural contract = the reference's myers_banded_kernel and callees (cudaaligner/src/myers_gpu.cu:78-255, 444-1032):
+// identical band choices, identical bit-vector band (pv / mv / score per 32-row word and target column, including the
+// worst-case fills at the band edges), identical backtrace tie-breaking (insertion, deletion, then diagonal) and RLE path.
+// The implementation is not the reference's:
+//   * for bands of <= 32 words (max_bandwidth <= 1024) column t-1 lives in registers: the hot loop issues no loads of
+//     pv/mv/score, only three coalesced 128-byte stores per column (12 B per word-column = the algorithmic bytes);
+//   * the multi-word addition resolves its carries with two warp ballots and one integer add instead of a shuffle loop;
+//   * the backtrace runs out of shared memory: the warp stages 32 target columns x band words with coalesced loads and
+//     walks them with popcount score reconstruction, instead of ~9 dependent global loads per step on one lane;
+//   * results are written to per-alignment slots, then compacted in input order (no atomics, no sort).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gwb200
+{
+namespace myers
+{
+
+typedef uint32_t WordType;
+constexpr int32_t kWord       = 32;
+constexpr int32_t kStageCols  = 32;
+constexpr uint32_t kFull      = 0xffffffffu;
+constexpr int32_t kOutOfBand  = INT32_MAX - 1; // myers_gpu.cu:448
+
+enum : int8_t
+{
+    st_match = 0,
+    st_mismatch,
+    st_insertion,
+    st_deletion
+};
+
+struct DeviceParams
+{
+    const char* seqs;
+    const int64_t* seq_starts;   // [2n+1]
+    const int32_t* max_bw;       // [n]
+    const int32_t* sched_index;  // [n] tasks, largest first
+    int32_t* sched_counter;      // [1]
+    int32_t n_alignments;
+    // per-CTA workspaces
+    WordType* pv;
+    WordType* mv;
+    int32_t* score;
+    int64_t ws_elems;            // elements per CTA in pv / mv / score
+    WordType* qpat;
+    int32_t qpat_elems;          // elements per CTA (>= 4 * ceil(max_query/32))
+    // per-alignment result slots: alignment i owns [seq_starts[2i], seq_starts[2i+2])
+    int8_t* slot_actions;
+    int32_t* slot_runs;
+    int32_t* path_len;           // [n]  number of RLE entries, 0 if none
+    uint32_t* metadata;          // [n]  index | is_optimal << 31
+    unsigned long long* cells;   // [1]  executed DP cells (sum over passes of band_width x target_size)
+};
+
+__device__ __forceinline__ int32_t ceil_div(int32_t a, int32_t b) { return (a + b - 1) / b; }
+
+// column-major matrix view, data[i + n_rows * j] (cf. batched_device_matrices.cuh:61-76)
+template <typename T>
+struct View
+{
+    T* data;
+    int32_t rows;
+    __device__ __forceinline__ T& operator()(int32_t i, int32_t j) const { return data[i + static_cast<int64_t>(rows) * j]; }
+};
+
+// get_query_pattern, myers_gpu.cu:210-241. qpat is [n_words x 4] column-major, char order A,C,T,G via (x >> 1) & 3.
+__device__ __forceinline__ WordType query_pattern(const WordType* qpat, int32_t n_words, int32_t idx, int32_t query_begin_offset, char x)
+{
+    const int32_t char_idx   = (x >> 1) & 0x3;
+    const int32_t idx_offset = query_begin_offset / kWord;
+    const int32_t shift      = query_begin_offset % kWord;
+    const WordType* col      = qpat + char_idx * n_words;
+    WordType r               = col[idx + idx_offset];
+    if (shift != 0)
+    {
+        r >>= shift;
+        if (idx + idx_offset + 1 < n_words)
+            r |= col[idx + idx_offset + 1] << (kWord - shift);
+    }
+    return r;
+}
+
+// Multi-word a + b over the lanes of `mask` (lane = word, little endian), carry out of the top lane dropped:
+// warp_add_sync, myers_gpu.cu:104-130, with the carries resolved by ballot arithmetic.
+__device__ __forceinline__ WordType warp_add(uint32_t mask, WordType a, WordType b, int32_t lane)
+{
+    const WordType s   = a + b;
+    const uint32_t G   = __ballot_sync(mask, s < a);       // generate
+    const uint32_t P   = __ballot_sync(mask, s == kFull);  // propagate
+    const uint32_t cin = (((G | P) + G) ^ P);              // carry INTO each lane
+    return s + ((cin >> lane) & 1u);
+}
+
+// Stage 1 + 2 of the Myers block update for one column (myers_advance_block[2], myers_gpu.cu:132-194).
+// Returns the horizontal delta at `hb` (x) and at `hb << 1` (y).
+__device__ __forceinline__ int2 advance_block(uint32_t mask, int32_t lane, WordType hb, WordType eq, WordType& pv, WordType& mv, int32_t carry_in)
+{
+    const WordType xv = eq | mv;
+    if (carry_in < 0)
+        eq |= WordType(1);
+    WordType xh = warp_add(mask, eq & pv, pv, lane);
+    xh          = (xh ^ pv) | eq;
+    WordType ph = mv | (~(xh | pv));
+    WordType mh = pv & xh;
+    int2 out;
+    out.x = ((ph & hb) == 0 ? 0 : 1) - ((mh & hb) == 0 ? 0 : 1);
+    out.y = ((ph & (hb << 1)) == 0 ? 0 : 1) - ((mh & (hb << 1)) == 0 ? 0 : 1);
+    // shift ph and mh left by one across the lanes (one shuffle carries both top bits)
+    const uint32_t tops = (ph >> 31) | ((mh >> 31) << 1);
+    const uint32_t in   = __shfl_up_sync(mask, tops, 1);
+    ph <<= 1;
+    mh <<= 1;
+    if (lane != 0)
+    {
+        ph |= (in & 1u);
+        mh |= (in >> 1);
+    }
+    if (carry_in < 0)
+        mh |= WordType(1);
+    if (carry_in > 0)
+        ph |= WordType(1);
+    pv = mh | (~(xv | ph));
+    mv = ph & xv;
+    return out;
+}
+
+// Fast path: band of <= 32 words, one word per lane, column t-1 held in registers.
+struct BandRegs
+{
+    WordType pv, mv;
+    int32_t sc;
+};
+
+__device__ __forceinline__ void horizontal_fast(uint32_t mask, int32_t lane, BandRegs& R, const View<WordType>& pvm, const View<WordType>& mvm,
+                                                const View<int32_t>& scm, const WordType* qpat, int32_t n_words_query, const char* target,
+                                                int32_t t_begin, int32_t t_end, int32_t width, int32_t n_words, int32_t pattern_idx_offset)
+{
+    const WordType hb = WordType(1) << (lane == (n_words - 1) ? width - (n_words - 1) * kWord - 1 : kWord - 1);
+    for (int32_t t = t_begin; t < t_end; ++t)
+    {
+        const char tc     = target[t - 1];
+        const WordType eq = query_pattern(qpat, n_words_query, lane, pattern_idx_offset, tc);
+        const int2 c      = advance_block(mask, lane, hb, eq, R.pv, R.mv, lane == 0 ? 1 : 0);
+        R.sc += c.x;
+        pvm(lane, t) = R.pv;
+        mvm(lane, t) = R.mv;
+        scm(lane, t) = R.sc;
+    }
+}
+
+__device__ __forceinline__ void diagonal_fast(uint32_t mask, int32_t lane, BandRegs& R, const View<WordType>& pvm, const View<WordType>& mvm,
+                                              const View<int32_t>& scm, const WordType* qpat, int32_t n_words_query, const char* target,
+                                              int32_t t_begin, int32_t t_end, int32_t band_width, int32_t n_words_band)
+{
+    const bool last      = lane == n_words_band - 1;
+    const WordType drb   = WordType(1) << (last ? band_width - (n_words_band - 1) * kWord - 2 : kWord - 2);
+    const WordType ddb   = drb << 1;
+    const bool has_above = (mask >> lane) > 1u;
+    for (int32_t t = t_begin; t < t_end; ++t)
+    {
+        // previous column shifted down by one row: warp_rightshift_sync on pv and mv (myers_gpu.cu:91-102, 705-706)
+        const uint32_t lows = (R.pv & 1u) | ((R.mv & 1u) << 1);
+        const uint32_t in   = __shfl_down_sync(mask, lows, 1);
+        WordType pv         = R.pv >> 1;
+        WordType mv         = R.mv >> 1;
+        if (has_above)
+        {
+            pv |= (in & 1u) << 31;
+            mv |= (in >> 1) << 31;
+        }
+        const char tc     = target[t - 1];
+        const WordType eq = query_pattern(qpat, n_words_query, lane, t - t_begin + 1, tc);
+        if (last)
+        {
+            // bits without a left neighbour: assume the worst case +1 (:721-726)
+            pv |= ddb;
+            mv &= ~ddb;
+        }
+        const int2 c             = advance_block(mask, lane, drb, eq, pv, mv, lane == 0 ? 1 : 0);
+        const int32_t delta_down = ((pv & ddb) == 0 ? 0 : 1) - ((mv & ddb) == 0 ? 0 : 1);
+        R.sc += c.x + delta_down;
+        R.pv = pv;
+        R.mv = mv;
+        pvm(lane, t) = pv;
+        mvm(lane, t) = mv;
+        scm(lane, t) = R.sc;
+    }
+}
+
+// General path: any number of band words, 32 words per warp iteration, previous column re-read from memory
+// (myers_compute_scores_horizontal_band_impl / _diagonal_band_impl, myers_gpu.cu:629-751).
+__device__ void horizontal_general(int32_t lane, const View<WordType>& pvm, const View<WordType>& mvm, const View<int32_t>& scm,
+                                   const WordType* qpat, int32_t n_words_query, const char* target, int32_t t_begin, int32_t t_end,
+                                   int32_t width, int32_t n_words, int32_t pattern_idx_offset)
+{
+    const int32_t n_iter = ceil_div(n_words, 32) * 32;
+    for (int32_t t = t_begin; t < t_end; ++t)
+    {
+        int32_t carry = lane == 0 ? 1 : 0;
+        const char tc = target[t - 1];
+        for (int32_t idx = lane; idx < n_iter; idx += 32)
+        {
+            if (idx < n_words)
+            {
+                const uint32_t mask = idx / 32 < n_words / 32 ? kFull : (1u << (n_words % 32)) - 1;
+                WordType pv         = pvm(idx, t - 1);
+                WordType mv         = mvm(idx, t - 1);
+                const WordType hb   = WordType(1) << (idx == (n_words - 1) ? width - (n_words - 1) * kWord - 1 : kWord - 1);
+                const WordType eq   = query_pattern(qpat, n_words_query, idx, pattern_idx_offset, tc);
+                const int2 c        = advance_block(mask, lane, hb, eq, pv, mv, carry);
+                scm(idx, t)         = scm(idx, t - 1) + c.x;
+                carry               = 0;
+                if (mask == kFull)
+                {
+                    const int32_t top = __shfl_sync(kFull, c.x, 31);
+                    if (lane == 0)
+                        carry = top;
+                }
+                pvm(idx, t) = pv;
+                mvm(idx, t) = mv;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ void diagonal_general(int32_t lane, const View<WordType>& pvm, const View<WordType>& mvm, const View<int32_t>& scm,
+                                 const WordType* qpat, int32_t n_words_query, const char* target, int32_t t_begin, int32_t t_end,
+                                 int32_t band_width, int32_t n_words_band)
+{
+    const int32_t n_iter = ceil_div(n_words_band, 32) * 32;
+    for (int32_t t = t_begin; t < t_end; ++t)
+    {
+        int32_t carry = lane == 0 ? 1 : 0;
+        const char tc = target[t - 1];
+        for (int32_t idx = lane; idx < n_iter; idx += 32)
+        {
+            const uint32_t mask = idx / 32 < n_words_band / 32 ? kFull : (1u << (n_words_band % 32)) - 1;
+            if (idx < n_words_band)
+            {
+                const WordType pvp  = pvm(idx, t - 1);
+                const WordType mvp  = mvm(idx, t - 1);
+                const uint32_t lows = (pvp & 1u) | ((mvp & 1u) << 1);
+                const uint32_t in   = __shfl_down_sync(mask, lows, 1);
+                WordType pv         = pvp >> 1;
+                WordType mv         = mvp >> 1;
+                if ((mask >> lane) > 1u)
+                {
+                    pv |= (in & 1u) << 31;
+                    mv |= (in >> 1) << 31;
+                }
+                if (lane == 31 && mask == kFull && idx < n_words_band - 1)
+                {
+                    pv |= pvm(idx + 1, t - 1) << 31;
+                    mv |= mvm(idx + 1, t - 1) << 31;
+                }
+                const WordType eq  = query_pattern(qpat, n_words_query, idx, t - t_begin + 1, tc);
+                const WordType drb = WordType(1) << (idx == (n_words_band - 1) ? band_width - (n_words_band - 1) * kWord - 2 : kWord - 2);
+                const WordType ddb = drb << 1;
+                if (idx == n_words_band - 1)
+                {
+                    pv |= ddb;
+                    mv &= ~ddb;
+                }
+                const int2 c             = advance_block(mask, lane, drb, eq, pv, mv, carry);
+                const int32_t delta_down = ((pv & ddb) == 0 ? 0 : 1) - ((mv & ddb) == 0 ? 0 : 1);
+                scm(idx, t)              = scm(idx, t - 1) + c.x + delta_down;
+                carry                    = 0;
+                if (mask == kFull)
+                {
+                    const int32_t top = __shfl_sync(kFull, c.y, 31);
+                    if (lane == 0)
+                        carry = top;
+                }
+                pvm(idx, t) = pv;
+                mvm(idx, t) = mv;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// myers_compute_scores_edit_dist_banded, myers_gpu.cu:753-846
+__device__ void compute_scores_banded(int32_t lane, int32_t& diagonal_begin, int32_t& diagonal_end, const View<WordType>& pvm,
+                                      const View<WordType>& mvm, const View<int32_t>& scm, const WordType* qpat, int32_t n_words_query,
+                                      const char* target, int32_t target_size, int32_t query_size, int32_t band_width, int32_t n_words_band,
+                                      int32_t p)
+{
+    int32_t sym = 0;
+    const bool full_myers = band_width >= query_size;
+    if (full_myers)
+    {
+        diagonal_begin = target_size + 1;
+        diagonal_end   = target_size + 1;
+    }
+    else
+    {
+        sym            = (band_width - min(1 + 2 * p + abs(target_size - query_size), query_size) == 0) ? 1 : 0;
+        diagonal_begin = query_size < target_size ? target_size - query_size + p + 2 : p + 2 + (1 - sym);
+        diagonal_end   = query_size < target_size ? query_size - p + sym : query_size - (query_size - target_size) - p + 1;
+    }
+    if (n_words_band <= 32)
+    {
+        if (lane < n_words_band)
+        {
+            const uint32_t mask = n_words_band == 32 ? kFull : (1u << n_words_band) - 1;
+            BandRegs R;
+            R.pv = ~WordType(0);
+            R.mv = 0;
+            R.sc = min((lane + 1) * kWord, band_width);
+            pvm(lane, 0) = R.pv;
+            mvm(lane, 0) = R.mv;
+            scm(lane, 0) = R.sc;
+            if (full_myers)
+            {
+                horizontal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, 1, target_size + 1, query_size, n_words_band, 0);
+            }
+            else
+            {
+                horizontal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, 1, diagonal_begin, band_width, n_words_band, 0);
+                diagonal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, diagonal_begin, diagonal_end, band_width, n_words_band);
+                horizontal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, diagonal_end, target_size + 1, band_width, n_words_band,
+                                query_size - band_width);
+            }
+        }
+        __syncwarp();
+        return;
+    }
+    for (int32_t idx = lane; idx < n_words_band; idx += 32)
+    {
+        pvm(idx, 0) = ~WordType(0);
+        mvm(idx, 0) = 0;
+        scm(idx, 0) = min((idx + 1) * kWord, band_width);
+    }
+    __syncwarp();
+    if (full_myers)
+    {
+        horizontal_general(lane, pvm, mvm, scm, qpat, n_words_query, target, 1, target_size + 1, query_size, n_words_band, 0);
+    }
+    else
+    {
+        horizontal_general(lane, pvm, mvm, scm, qpat, n_words_query, target, 1, diagonal_begin, band_width, n_words_band, 0);
+        diagonal_general(lane, pvm, mvm, scm, qpat, n_words_query, target, diagonal_begin, diagonal_end, band_width, n_words_band);
+        horizontal_general(lane, pvm, mvm, scm, qpat, n_words_query, target, diagonal_end, target_size + 1, band_width, n_words_band,
+                           query_size - band_width);
+    }
+}
+
+// Accessor for the backtrace: either the shared-memory stage (bands of <= 32 words) or global memory.
+struct Stage
+{
+    WordType* s_pv; // [kStageCols][32]
+    WordType* s_mv;
+    int32_t* s_sc;
+    View<WordType> pvm, mvm;
+    View<int32_t> scm;
+    int32_t n_words_band;
+    int32_t jlo, jhi; // staged columns [jlo, jhi]; jhi < jlo => nothing staged
+    bool use_smem;
+    WordType last_entry_mask;
+
+    __device__ __forceinline__ void refill(int32_t j, int32_t lane)
+    {
+        // make columns [j - kStageCols + 1, j] resident (clamped at 0)
+        __syncwarp();
+        jhi = j;
+        jlo = max(0, j - kStageCols + 1);
+        if (lane < n_words_band)
+        {
+            for (int32_t c = 0; c <= jhi - jlo; c++)
+            {
+                s_pv[c * 32 + lane] = pvm(lane, jlo + c);
+                s_mv[c * 32 + lane] = mvm(lane, jlo + c);
+                s_sc[c * 32 + lane] = scm(lane, jlo + c);
+            }
+        }
+        __syncwarp();
+    }
+    // get_myers_score, myers_gpu.cu:243-255
+    __device__ __forceinline__ int32_t get(int32_t i, int32_t j) const
+    {
+        const int32_t word_idx = (i - 1) / kWord;
+        const int32_t bit_idx  = (i - 1) % kWord;
+        WordType mask          = (~WordType(1)) << bit_idx;
+        if (word_idx == n_words_band - 1)
+            mask &= last_entry_mask;
+        int32_t s;
+        WordType p, m;
+        if (use_smem)
+        {
+            const int32_t o = (j - jlo) * 32 + word_idx;
+            s = s_sc[o];
+            p = s_pv[o];
+            m = s_mv[o];
+        }
+        else
+        {
+            s = scm(word_idx, j);
+            p = pvm(word_idx, j);
+            m = mvm(word_idx, j);
+        }
+        return s - __popc(mask & p) + __popc(mask & m);
+    }
+};
+
+struct RleWriter
+{
+    int8_t* path;
+    int32_t* count;
+    int32_t pos;
+    int32_t prev_r;
+    int32_t r_count;
+    bool writer;
+    __device__ __forceinline__ void change(int32_t r)
+    {
+        if (prev_r != r)
+        {
+            if (prev_r != -1)
+            {
+                if (writer)
+                {
+                    path[pos]  = static_cast<int8_t>(prev_r);
+                    count[pos] = r_count;
+                }
+                ++pos;
+            }
+            prev_r  = r;
+            r_count = 0;
+        }
+    }
+};
+
+// myers_backtrace_banded, myers_gpu.cu:444-627. All lanes walk redundantly (warp-uniform control flow) on staged data;
+// lane 0 writes the RLE path. Returns the number of RLE entries.
+__device__ int32_t backtrace_banded(int32_t lane, Stage& S, int8_t* path, int32_t* path_count, int32_t diagonal_begin, int32_t diagonal_end,
+                                    int32_t band_width, int32_t target_size)
+{
+    int32_t i = band_width;
+    int32_t j = target_size;
+    S.last_entry_mask = band_width % kWord != 0 ? (WordType(1) << (band_width % kWord)) - 1 : ~WordType(0);
+    int32_t last_diagonal_score = kOutOfBand;
+    if (diagonal_end >= 2)
+    {
+        if (S.use_smem)
+            S.refill(diagonal_end - 2, lane);
+        last_diagonal_score = S.get(1, diagonal_end - 2) + 2;
+    }
+    if (S.use_smem)
+        S.refill(j, lane);
+    int32_t myscore = i > 0 ? S.scm((i - 1) / kWord, j) : 0;
+    RleWriter W{path, path_count, 0, -1, 0, lane == 0};
+
+    while (j >= diagonal_end)
+    {
+        if (S.use_smem && j - 1 < S.jlo && j >= 1)
+            S.refill(j, lane);
+        int32_t r;
+        const int32_t above = i <= 1 ? (last_diagonal_score + j - diagonal_end) : S.get(i - 1, j);
+        const int32_t diag  = i <= 1 ? (last_diagonal_score + j - 1 - diagonal_end) : S.get(i - 1, j - 1);
+        const int32_t left  = i < 1 ? (last_diagonal_score + j - 1 - diagonal_end) : S.get(i, j - 1);
+        if (left + 1 == myscore)
+        {
+            r       = st_insertion;
+            myscore = left;
+            --j;
+        }
+        else if (above + 1 == myscore)
+        {
+            r       = st_deletion;
+            myscore = above;
+            --i;
+        }
+        else
+        {
+            r       = (diag == myscore ? st_match : st_mismatch);
+            myscore = diag;
+            --i;
+            --j;
+        }
+        W.change(r);
+        ++W.r_count;
+    }
+    while (j >= diagonal_begin)
+    {
+        if (S.use_smem && j - 1 < S.jlo && j >= 1)
+            S.refill(j, lane);
+        int32_t r;
+        const int32_t above = i <= 1 ? kOutOfBand : S.get(i - 1, j);
+        const int32_t diag  = i <= 0 ? j - 1 : S.get(i, j - 1);
+        const int32_t left  = i >= band_width ? kOutOfBand : S.get(i + 1, j - 1);
+        if (left + 1 == myscore)
+        {
+            r       = st_insertion;
+            myscore = left;
+            ++i;
+            --j;
+        }
+        else if (above + 1 == myscore)
+        {
+            r       = st_deletion;
+            myscore = above;
+            --i;
+        }
+        else
+        {
+            r       = (diag == myscore ? st_match : st_mismatch);
+            myscore = diag;
+            --j;
+        }
+        W.change(r);
+        ++W.r_count;
+    }
+    while (i > 0 && j > 0)
+    {
+        if (S.use_smem && j - 1 < S.jlo)
+            S.refill(j, lane);
+        int32_t r;
+        const int32_t above = i == 1 ? j : S.get(i - 1, j);
+        const int32_t diag  = i == 1 ? j - 1 : S.get(i - 1, j - 1);
+        const int32_t left  = i > band_width ? kOutOfBand : S.get(i, j - 1);
+        if (left + 1 == myscore)
+        {
+            r       = st_insertion;
+            myscore = left;
+            --j;
+        }
+        else if (above + 1 == myscore)
+        {
+            r       = st_deletion;
+            myscore = above;
+            --i;
+        }
+        else
+        {
+            r       = (diag == myscore ? st_match : st_mismatch);
+            myscore = diag;
+            --i;
+            --j;
+        }
+        W.change(r);
+        ++W.r_count;
+    }
+    if (i > 0)
+    {
+        W.change(st_deletion);
+        W.r_count += i;
+    }
+    if (j > 0)
+    {
+        W.change(st_insertion);
+        W.r_count += j;
+    }
+    if (W.r_count != 0)
+    {
+        if (W.writer)
+        {
+            path[W.pos]       = static_cast<int8_t>(W.prev_r);
+            path_count[W.pos] = W.r_count;
+        }
+        ++W.pos;
+    }
+    __syncwarp();
+    return W.pos;
+}
+
+__device__ __forceinline__ int32_t fetch_task(const DeviceParams& P, int32_t lane)
+{
+    int32_t k = 0;
+    if (lane == 0)
+        k = atomicAdd(P.sched_counter, 1);
+    k = __shfl_sync(kFull, k, 0);
+    return k < P.n_alignments ? P.sched_index[k] : P.n_alignments;
+}
+
+// myers_banded_kernel, myers_gpu.cu:862-1032
+__global__ void __launch_bounds__(32, 16) myers_banded_kernel(const DeviceParams P)
+{
+    __shared__ WordType s_pv[kStageCols * 32];
+    __shared__ WordType s_mv[kStageCols * 32];
+    __shared__ int32_t s_sc[kStageCols * 32];
+
+    const int32_t lane = threadIdx.x;
+    WordType* qpat     = P.qpat + static_cast<int64_t>(blockIdx.x) * P.qpat_elems;
+    WordType* pv_ws    = P.pv + static_cast<int64_t>(blockIdx.x) * P.ws_elems;
+    WordType* mv_ws    = P.mv + static_cast<int64_t>(blockIdx.x) * P.ws_elems;
+    int32_t* sc_ws     = P.score + static_cast<int64_t>(blockIdx.x) * P.ws_elems;
+    unsigned long long my_cells = 0;
+
+    int32_t a = fetch_task(P, lane);
+    while (a < P.n_alignments)
+    {
+        const char* const query   = P.seqs + P.seq_starts[2 * a];
+        const char* const target  = P.seqs + P.seq_starts[2 * a + 1];
+        const int32_t query_size  = static_cast<int32_t>(P.seq_starts[2 * a + 1] - P.seq_starts[2 * a]);
+        const int32_t target_size = static_cast<int32_t>(P.seq_starts[2 * a + 2] - P.seq_starts[2 * a + 1]);
+        const int32_t n_words     = ceil_div(query_size, kWord);
+        const int32_t max_bandwidth = P.max_bw[a];
+        int8_t* out_actions       = P.slot_actions + P.seq_starts[2 * a];
+        int32_t* out_runs         = P.slot_runs + P.seq_starts[2 * a];
+
+        if (max_bandwidth - 1 < abs(target_size - query_size) && query_size != 0 && target_size != 0)
+        {
+            if (lane == 0)
+            {
+                P.path_len[a] = 0;
+                P.metadata[a] = static_cast<uint32_t>(a);
+            }
+            a = fetch_task(P, lane);
+            continue;
+        }
+        if (target_size == 0 || query_size == 0)
+        {
+            if (lane == 0)
+            {
+                if (query_size == 0 && target_size == 0)
+                {
+                    P.path_len[a] = 0;
+                }
+                else
+                {
+                    P.path_len[a]  = 1;
+                    out_actions[0] = query_size == 0 ? st_insertion : st_deletion;
+                    out_runs[0]    = query_size + target_size;
+                }
+                P.metadata[a] = static_cast<uint32_t>(a) | (1u << 31);
+            }
+            a = fetch_task(P, lane);
+            continue;
+        }
+        __syncwarp();
+        // query bit patterns, [n_words x 4] with character order A,C,T,G (:938-947)
+        for (int32_t idx = lane; idx < n_words; idx += 32)
+        {
+            const int32_t off   = idx * kWord;
+            const int32_t max_i = min(query_size - off, kWord);
+            WordType rA = 0, rC = 0, rT = 0, rG = 0;
+            for (int32_t i = 0; i < max_i; ++i)
+            {
+                const char c = query[off + i];
+                rA |= static_cast<WordType>(c == 'A') << i;
+                rC |= static_cast<WordType>(c == 'C') << i;
+                rT |= static_cast<WordType>(c == 'T') << i;
+                rG |= static_cast<WordType>(c == 'G') << i;
+            }
+            qpat[idx]               = rA;
+            qpat[n_words + idx]     = rC;
+            qpat[2 * n_words + idx] = rT;
+            qpat[3 * n_words + idx] = rG;
+        }
+        __syncwarp();
+
+        // Ukkonen band doubling (:955-1002)
+        int32_t max_distance_estimate = max(1, abs(target_size - query_size) + min(target_size, query_size) / 20);
+        View<WordType> pvm{pv_ws, 0}, mvm{mv_ws, 0};
+        View<int32_t> scm{sc_ws, 0};
+        int32_t diagonal_begin = -1, diagonal_end = -1, band_width = 0, n_words_band = 0;
+        while (1)
+        {
+            int32_t p              = min(min(target_size, query_size), (max_distance_estimate - abs(target_size - query_size)) / 2);
+            int32_t band_width_new = min(1 + 2 * p + abs(target_size - query_size), query_size);
+            if (band_width_new % kWord == 1 && band_width_new != query_size)
+            {
+                p += 1;
+                band_width_new = min(1 + 2 * p + abs(target_size - query_size), query_size);
+            }
+            if (band_width_new > max_bandwidth)
+            {
+                band_width_new = max_bandwidth;
+                p              = (band_width_new - 1 - abs(target_size - query_size)) / 2;
+            }
+            const int32_t nwb = ceil_div(band_width_new, kWord);
+            if (static_cast<int64_t>(nwb) * static_cast<int64_t>(target_size + 1) > P.ws_elems)
+            {
+                band_width = -band_width;
+                break;
+            }
+            band_width   = band_width_new;
+            n_words_band = nwb;
+            pvm.rows     = nwb;
+            mvm.rows     = nwb;
+            scm.rows     = nwb;
+            my_cells += static_cast<unsigned long long>(band_width) * static_cast<unsigned long long>(target_size);
+            compute_scores_banded(lane, diagonal_begin, diagonal_end, pvm, mvm, scm, qpat, n_words, target, target_size, query_size, band_width,
+                                  nwb, p);
+            __syncwarp();
+            const int32_t cur_edit_distance = nwb > 0 ? scm(nwb - 1, target_size) : target_size;
+            if (cur_edit_distance <= max_distance_estimate || band_width == query_size)
+                break;
+            if (band_width == max_bandwidth)
+            {
+                band_width = -band_width;
+                break;
+            }
+            max_distance_estimate *= 2;
+        }
+        int32_t path_length = 0;
+        if (band_width != 0)
+        {
+            Stage S;
+            S.s_pv         = s_pv;
+            S.s_mv         = s_mv;
+            S.s_sc         = s_sc;
+            S.pvm          = pvm;
+            S.mvm          = mvm;
+            S.scm          = scm;
+            S.n_words_band = n_words_band;
+            S.jlo          = 0;
+            S.jhi          = -1;
+            S.use_smem     = n_words_band <= 32;
+            path_length    = backtrace_banded(lane, S, out_actions, out_runs, diagonal_begin, diagonal_end, abs(band_width), target_size);
+        }
+        if (lane == 0)
+        {
+            P.path_len[a] = path_length;
+            P.metadata[a] = static_cast<uint32_t>(a) | ((band_width > 0) ? (1u << 31) : 0u);
+        }
+        a = fetch_task(P, lane);
+        __syncwarp();
+    }
+    if (lane == 0 && my_cells)
+        atomicAdd(P.cells, my_cells);
+}
+
+// Exclusive scan of path_len -> offsets[n+1] (single CTA; n is at most a few million).
+__global__ void offsets_kernel(const int32_t* path_len, int32_t n, int32_t* offsets)
+{
+    __shared__ int32_t s_warp[32];
+    __shared__ int32_t s_base;
+    const int32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0)
+        s_base = 0;
+    __syncthreads();
+    for (int32_t start = 0; start < n; start += blockDim.x)
+    {
+        const int32_t i = start + tid;
+        int32_t v       = i < n ? path_len[i] : 0;
+        int32_t x       = v;
+        for (int32_t d = 1; d < 32; d <<= 1)
+        {
+            int32_t o = __shfl_up_sync(kFull, x, d);
+            if (lane >= d)
+                x += o;
+        }
+        if (lane == 31)
+            s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0)
+        {
+            int32_t w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0;
+            for (int32_t d = 1; d < 32; d <<= 1)
+            {
+                int32_t o = __shfl_up_sync(kFull, w, d);
+                if (lane >= d)
+                    w += o;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int32_t base = s_base + (wid > 0 ? s_warp[wid - 1] : 0);
+        if (i < n)
+            offsets[i] = base + x - v;
+        __syncthreads();
+        if (tid == 0)
+            s_base += s_warp[(blockDim.x >> 5) - 1];
+        __syncthreads();
+    }
+    if (tid == 0)
+        offsets[n] = s_base;
+}
+
+// Packs the per-alignment slots into contiguous DeviceAlignmentsPtrs-style arrays (aligner.hpp:62-72), input order.
+__global__ void compact_kernel(DeviceParams P, const int32_t* offsets, int8_t* actions, int32_t* runs)
+{
+    const int32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int32_t lane = threadIdx.x & 31;
+    if (warp >= P.n_alignments)
+        return;
+    const int32_t len = P.path_len[warp];
+    const int64_t src = P.seq_starts[2 * warp];
+    const int32_t dst = offsets[warp];
+    for (int32_t i = lane; i < len; i += 32)
+    {
+        actions[dst + i] = P.slot_actions[src + i];
+        runs[dst + i]    = P.slot_runs[src + i];
+    }
+}
+
+} // namespace myers
+} // namespace gwb200

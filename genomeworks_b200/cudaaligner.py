@@ -1,0 +1,249 @@
+"""Python mirror of pygenomeworks' cudaaligner shim (pygenomeworks/genomeworks/cudaaligner/cudaaligner.pyx) over the gw-b200
+C ABI, plus the FixedBandAligner surface (cudaaligner/include/.../aligner.hpp:148-219) the reference's Python shim lacks.
+
+CudaAlignerBatch keeps the deprecated-factory signature (max_query_length, max_target_length, max_alignments, ...). The
+reference serves it with AlignerGlobalHirschbergMyers; this engine serves it with the banded Myers aligner at a bandwidth
+that covers the whole query (full Myers, exact), whose tie-breaking (insertion, deletion, diagonal) reproduces the CIGARs the
+reference's Python tests pin (tests/test_oracle_aligner.py)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+success = 0
+uninitialized = 1
+exceeded_max_alignments = 2
+exceeded_max_length = 3
+exceeded_max_alignment_difference = 4
+generic_error = 5
+
+match, mismatch, insertion, deletion = 0, 1, 2, 3
+global_alignment = 0
+
+_STATUS = ["success", "uninitialized", "exceeded_max_alignments", "exceeded_max_length", "exceeded_max_alignment_difference",
+           "generic_error"]
+_BASIC = {0: "M", 1: "M", 2: "I", 3: "D"}
+_EXT = {0: "=", 1: "X", 2: "I", 3: "D"}
+
+
+def status_to_str(status):
+    if 0 <= int(status) < len(_STATUS):
+        return _STATUS[int(status)]
+    raise RuntimeError("Unknown error status : " + str(status))
+
+
+def _cigar(actions, runs, extended=False):
+    """AlignmentImpl::convert_to_cigar over the RLE form (cudaaligner/src/alignment_impl.cpp:99-153)."""
+    if extended:
+        return "".join("%d%s" % (int(r), _EXT[int(a)]) for a, r in zip(actions, runs))
+    out, last, cnt = [], None, 0
+    for a, r in zip(actions, runs):
+        c = _BASIC[int(a)]
+        if c == last:
+            cnt += int(r)
+        else:
+            if last is not None:
+                out.append("%d%s" % (cnt, last))
+            last, cnt = c, int(r)
+    if last is not None:
+        out.append("%d%s" % (cnt, last))
+    return "".join(out)
+
+
+class Alignment:
+    """What cudaaligner::Alignment exposes (alignment.hpp:55-111)."""
+
+    def __init__(self, query, target, status, is_optimal, actions, runs):
+        self.query = query
+        self.target = target
+        self.status = status
+        self.is_optimal = bool(is_optimal)
+        self.actions = actions
+        self.runlengths = runs
+
+    def convert_to_cigar(self, extended=False):
+        return _cigar(self.actions, self.runlengths, extended)
+
+    def get_edit_distance(self):
+        return int(sum(int(r) for a, r in zip(self.actions, self.runlengths) if int(a) != match))
+
+    def get_alignment(self):
+        out = []
+        for a, r in zip(self.actions, self.runlengths):
+            out.extend([int(a)] * int(r))
+        return out
+
+    def format_alignment(self):
+        """(query line, pairing line, target line), cf. AlignmentImpl::format_alignment."""
+        q, p, t = [], [], []
+        qi = ti = 0
+        for s in self.get_alignment():
+            if s in (match, mismatch):
+                q.append(self.query[qi])
+                t.append(self.target[ti])
+                p.append("|" if s == match else "x")
+                qi += 1
+                ti += 1
+            elif s == insertion:
+                q.append("-")
+                t.append(self.target[ti])
+                p.append(" ")
+                ti += 1
+            else:
+                q.append(self.query[qi])
+                t.append("-")
+                p.append(" ")
+                qi += 1
+        return ("".join(q), "".join(p), "".join(t))
+
+
+class CudaAlignment:
+    """pygenomeworks' result record (cudaaligner.pyx:57-126)."""
+
+    def __init__(self, query, target, cigar, alignment_type, status, alignment, format_alignment):
+        self.query = query
+        self.target = target
+        self.cigar = cigar
+        self.alignment_type = "global"
+        self.status = status
+        names = {match: "m", mismatch: "mm", insertion: "i", deletion: "d"}
+        self.alignment = [names[s] for s in alignment]
+        self.format_alignment = format_alignment
+
+    def __str__(self):
+        return "{}\n{}\n{}\n".format(self.format_alignment[0], self.format_alignment[1], self.format_alignment[2])
+
+
+class FixedBandAligner:
+    """create_aligner(AlignmentType::global_alignment, max_bandwidth, stream, device_id, max_device_memory) -- aligner.hpp:208-219."""
+
+    def __init__(self, max_bandwidth, stream=None, device_id=0, max_device_memory=-1):
+        self._h = C.c_void_p()
+        st = None
+        if stream is not None:
+            st = stream.stream if hasattr(stream, "stream") else stream.cuda_stream
+        self.stream = stream
+        self._pairs = []
+        self._results = []
+        check(lib().gwb200_aligner_create(C.byref(self._h), C.c_int32(max_bandwidth), C.c_void_p(st), C.c_int32(device_id),
+                                          C.c_int64(int(max_device_memory))))
+
+    def add_alignment(self, query, target, max_bandwidth=0, reverse_complement_query=False, reverse_complement_target=False):
+        q = query.encode("utf-8") if isinstance(query, str) else bytes(query)
+        t = target.encode("utf-8") if isinstance(target, str) else bytes(target)
+        rc = check(lib().gwb200_aligner_add_alignment(self._h, C.c_int32(max_bandwidth), q, C.c_int32(len(q)), t, C.c_int32(len(t)),
+                                                      C.c_int32(1 if reverse_complement_query else 0),
+                                                      C.c_int32(1 if reverse_complement_target else 0)))
+        if rc == success:
+            self._pairs.append((q, t))
+        return rc
+
+    def align_all(self):
+        return check(lib().gwb200_aligner_align_all(self._h))
+
+    def sync_alignments(self, want_strings=True):
+        rc = check(lib().gwb200_aligner_sync_alignments(self._h))
+        self._results = []
+        st, opt, nr = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        for i, (q, t) in enumerate(self._pairs):
+            check(lib().gwb200_aligner_result_info(self._h, C.c_int32(i), C.byref(st), C.byref(opt), C.byref(nr)))
+            a = np.zeros(max(nr.value, 1), dtype=np.int8)
+            r = np.zeros(max(nr.value, 1), dtype=np.int32)
+            check(lib().gwb200_aligner_result_runs(self._h, C.c_int32(i), a.ctypes.data, r.ctypes.data))
+            self._results.append(Alignment(q.decode() if want_strings else q, t.decode() if want_strings else t, st.value, opt.value,
+                                           a[:nr.value].copy(), r[:nr.value].copy()))
+        self._pairs = []
+        return rc
+
+    def get_alignments(self):
+        return list(self._results)
+
+    def num_alignments(self):
+        return lib().gwb200_aligner_num_alignments(self._h)
+
+    def reset(self):
+        self._pairs = []
+        self._results = []
+        check(lib().gwb200_aligner_reset(self._h))
+
+    def reset_max_bandwidth(self, max_bandwidth):
+        self._pairs = []
+        check(lib().gwb200_aligner_reset_max_bandwidth(self._h, C.c_int32(max_bandwidth)))
+
+    def free_temporary_device_buffers(self):
+        check(lib().gwb200_aligner_free_temporary_device_buffers(self._h))
+
+    def last_cells(self):
+        return int(lib().gwb200_aligner_last_cells(self._h))
+
+    def last_kernel_ms(self):
+        return float(lib().gwb200_aligner_last_kernel_ms(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().gwb200_aligner_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaAlignerBatch:
+    """pygenomeworks.CudaAlignerBatch (cudaaligner.pyx:129-260): deprecated-factory signature."""
+
+    def __init__(self, max_query_length, max_target_length, max_alignments, alignment_type="global", stream=None, device_id=0,
+                 max_device_memory_allocator_caching_size=-1, *args, **kwargs):
+        if alignment_type != "global":
+            raise RuntimeError("Unknown alignment_type provided. Must be global.")
+        if stream is not None and not (hasattr(stream, "stream") or hasattr(stream, "cuda_stream")):
+            raise RuntimeError("Type for stream option must be CudaStream")
+        self.max_query_length = max_query_length
+        self.max_target_length = max_target_length
+        self.max_alignments = max_alignments
+        bw = max(max_query_length, max_target_length, 2)
+        if bw % 32 == 1:
+            bw += 1
+        self._aligner = FixedBandAligner(bw, stream=stream, device_id=device_id, max_device_memory=max_device_memory_allocator_caching_size)
+        self.stream = stream
+
+    def add_alignment(self, query, target):
+        # AlignerGlobal::add_alignment admission (cudaaligner/src/aligner_global.cpp:50-86)
+        if len(query) > self.max_query_length or len(target) > self.max_target_length:
+            return exceeded_max_length
+        if self._aligner.num_alignments() >= self.max_alignments:
+            return exceeded_max_alignments
+        return self._aligner.add_alignment(query, target)
+
+    def align_all(self):
+        self._aligner.align_all()
+
+    def get_alignments(self):
+        self._aligner.sync_alignments()
+        out = []
+        for a in self._aligner.get_alignments():
+            out.append(CudaAlignment(a.query, a.target, a.convert_to_cigar(), global_alignment, a.status, a.get_alignment(),
+                                     a.format_alignment()))
+        return out
+
+    def reset(self):
+        self._aligner.reset()
+
+
+def smoke_check():
+    """Used by __graft_entry__.smoke(): one alignment on the device against the CPU oracle."""
+    import oracle_lib as ol
+    q = "ACGTTGCATGCATGGCATTACGATCGATCGATTTAGCAGCTAGCTAGTCGATGCTAGCTAGCTAGTCGATCGAT" * 6
+    t = q[:100] + "TT" + q[100:250] + q[260:]
+    al = FixedBandAligner(64)
+    assert al.add_alignment(q, t) == success
+    al.align_all()
+    al.sync_alignments()
+    r = al.get_alignments()[0]
+    o = ol.myers_align(q, t, 64)
+    assert r.status == o["status"] and int(r.is_optimal) == o["is_optimal"] and r.convert_to_cigar() == o["cigar"], (r.convert_to_cigar(), o["cigar"])
+    print("smoke: banded Myers CIGAR matches the oracle:", r.convert_to_cigar()[:60])
+    al.close()

@@ -165,3 +165,51 @@ def topsort(out_edges):
     out = np.zeros(n, dtype=np.int32)
     lib().oracle_topsort(C.c_int32(n), _p(off, C.c_int32), _p(adj_a, C.c_int32), _p(out, C.c_int32))
     return [int(x) for x in out]
+
+
+# ---- banded Myers aligner oracle -------------------------------------------------------------------
+ACTION_CHARS_BASIC = {0: "M", 1: "M", 2: "I", 3: "D"}
+ACTION_CHARS_EXT = {0: "=", 1: "X", 2: "I", 3: "D"}
+
+
+def cigar_from_runs(actions, runs, extended=False):
+    """AlignmentImpl::convert_to_cigar on the RLE representation (cudaaligner/src/alignment_impl.cpp:99-153)."""
+    tab = ACTION_CHARS_EXT if extended else ACTION_CHARS_BASIC
+    out = []
+    last, cnt = None, 0
+    for a, r in zip(actions, runs):
+        c = tab[int(a)]
+        if extended:
+            out.append("%d%s" % (int(r), c))
+            continue
+        if c == last:
+            cnt += int(r)
+        else:
+            if last is not None:
+                out.append("%d%s" % (cnt, last))
+            last, cnt = c, int(r)
+    if not extended and last is not None:
+        out.append("%d%s" % (cnt, last))
+    return "".join(out)
+
+
+def edit_distance_from_runs(actions, runs):
+    """AlignmentImpl::get_edit_distance (alignment_impl.cpp:218-234)."""
+    return int(sum(int(r) for a, r in zip(actions, runs) if int(a) != 0))
+
+
+def myers_align(query, target, max_bandwidth, max_elements_per_matrix=0):
+    q = query.encode() if isinstance(query, str) else bytes(query)
+    t = target.encode() if isinstance(target, str) else bytes(target)
+    n = len(q) + len(t) + 4
+    actions = np.zeros(n, dtype=np.int8)
+    runs = np.zeros(n, dtype=np.int32)
+    status = C.c_int32(0)
+    opt = C.c_int32(0)
+    cells = C.c_int64(0)
+    k = lib().oracle_myers_banded_align(C.c_char_p(q), C.c_int32(len(q)), C.c_char_p(t), C.c_int32(len(t)), C.c_int32(max_bandwidth),
+                                        C.c_int64(max_elements_per_matrix), C.byref(status), C.byref(opt), _p(actions, C.c_int8),
+                                        _p(runs, C.c_int32), C.byref(cells))
+    a, r = actions[:k].copy(), runs[:k].copy()
+    return dict(status=status.value, is_optimal=opt.value, actions=a, runs=r, cigar=cigar_from_runs(a, r),
+                cigar_extended=cigar_from_runs(a, r, True), edit_distance=edit_distance_from_runs(a, r), cells=cells.value)

@@ -79,7 +79,7 @@ def ref_poa_run(win_nseq, seq_len, seq_data, max_seq_size, max_seq_per_poa, band
     return res
 
 
-def ref_aligner_run(q_len, q_data, t_len, t_data, max_bandwidth, max_device_memory=-1, cigar_stride=None):
+def ref_aligner_run(q_len, q_data, t_len, t_data, max_bandwidth, max_device_memory=6 << 30, cigar_stride=None):
     q_len = np.ascontiguousarray(q_len, dtype=np.int32)
     t_len = np.ascontiguousarray(t_len, dtype=np.int32)
     q_data = np.ascontiguousarray(q_data, dtype=np.uint8)
