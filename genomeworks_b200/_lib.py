@@ -59,6 +59,8 @@ def lib():
     L.gwb200_poa_batch_last_cells.restype = C.c_int64
     L.gwb200_poa_batch_last_kernel_ms.argtypes = [C.c_void_p]
     L.gwb200_poa_batch_last_kernel_ms.restype = C.c_float
+    L.gwb200_poa_batch_enable_timers.argtypes = [C.c_void_p, C.c_int32]
+    L.gwb200_poa_batch_get_timers.argtypes = [C.c_void_p, C.c_void_p]
     L.gwb200_device_fdividef.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(L, "gwb200_aligner_create"):
         L.gwb200_aligner_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, C.c_int64]

@@ -7,6 +7,9 @@
 #include "../../include/gwb200.h"
 #include "common.cuh"
 #include "poa_kernels.cuh"
+#include "poa_kernels_v2.cuh"
+
+#include <cstdlib>
 
 #include <algorithm>
 #include <cstring>
@@ -87,6 +90,11 @@ struct gwb200_poa_batch
     // device
     uint8_t* d_block = nullptr;
     DeviceParams P{};
+    V2Extra X{};
+    bool use_v2 = true;
+    int32_t nw_override = 0;
+    bool timers_on = false;
+    unsigned long long* d_timers = nullptr;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool launched = false;
@@ -135,7 +143,10 @@ Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz,
         d += static_cast<int64_t>(s.stack_capacity) * sz;
         d += static_cast<int64_t>(c.max_sequences_per_poa) * c.max_consensus_size;
     }
-    d += 256 * 32; // carving alignment slack
+    d += (mn + 1) * 16;                                   // v2 row metadata
+    d += (align_up(std::max(c.max_sequence_size, 1), 4) + 8ll) * sz; // v2 read -> node map
+    d += 64;                                             // phase timers
+    d += 256 * 36; // carving alignment slack
     s.dev_per_poa    = d;
     s.dev_per_matrix = static_cast<int64_t>(c.matrix_sequence_dimension) * mn * score_bytes;
     int64_t h        = s.seq_bytes_per_poa * 2 + 4ll * c.max_sequences_per_poa + sizeof(WindowInfo) + c.max_consensus_size * 3ll + 4 * 3 + 8;
@@ -149,10 +160,49 @@ template <typename ScoreT, typename SizeT>
 void launch_typed(gwb200_poa_batch* b)
 {
     dim3 grid(b->poa_count), block(32);
-    if (b->msa)
-        poa_window_kernel<ScoreT, SizeT, true><<<grid, block, 0, b->stream>>>(b->P);
+    if (b->use_v2)
+    {
+        b->X.timers = b->timers_on ? b->d_timers : nullptr;
+        if (b->timers_on)
+            cudaMemsetAsync(b->d_timers, 0, sizeof(unsigned long long) * 8 * b->poa_count, b->stream);
+        // warps per window: one per 128-column band chunk, at most 4; chunks per warp bounded by the widest band the mode can
+        // reach (adaptive bands grow up to 1536 = 12 chunks)
+        const bool adaptive   = b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND && b->cfg.alignment_band_width < kMaxAdaptiveBW;
+        const int32_t nchunks = adaptive ? kMaxAdaptiveBW / 128 : std::max(1, b->cfg.alignment_band_width / 128);
+        // measured on B200 (profiles/): up to 2 chunks one warp is fastest (no CTA barriers); wider bands use 4 warps
+        int32_t nw            = nchunks >= 3 ? 4 : 1;
+        if (b->cfg.band_mode == GWB200_POA_FULL_BAND)
+            nw = 1;
+        if (b->nw_override > 0 && !adaptive && nchunks <= 4)
+            nw = b->nw_override; // development switch; MAXC = 1 kernels need nw >= nchunks, checked below
+        const int32_t smem = b->X.pool_bytes;
+#define GWB200_LAUNCH_V2(NWv, MAXCv)                                                                          \
+    do                                                                                                        \
+    {                                                                                                         \
+        auto kfn = poa_window_kernel_v2<ScoreT, SizeT, NWv, MAXCv>;                                           \
+        if (smem > 48 * 1024)                                                                                 \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                     \
+        kfn<<<grid, 32 * NWv, smem, b->stream>>>(b->P, b->X);                                                  \
+    } while (0)
+        if (nw == 1 && nchunks == 2)
+            GWB200_LAUNCH_V2(1, 2);
+        else if (nchunks > 4 || nw < std::min(nchunks, 4))
+            GWB200_LAUNCH_V2(4, 3);
+        else if (nw == 4)
+            GWB200_LAUNCH_V2(4, 1);
+        else if (nw == 2)
+            GWB200_LAUNCH_V2(2, 1);
+        else
+            GWB200_LAUNCH_V2(1, 1);
+#undef GWB200_LAUNCH_V2
+    }
     else
-        poa_window_kernel<ScoreT, SizeT, false><<<grid, block, 0, b->stream>>>(b->P);
+    {
+        if (b->msa)
+            poa_window_kernel<ScoreT, SizeT, true><<<grid, block, 0, b->stream>>>(b->P);
+        else
+            poa_window_kernel<ScoreT, SizeT, false><<<grid, block, 0, b->stream>>>(b->P);
+    }
     count_launch();
 }
 
@@ -453,6 +503,12 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
             P.stack_capacity = sz.stack_capacity;
             P.msa_out        = dc.take<uint8_t>(n * cfg->max_sequences_per_poa * mc);
         }
+        b->X.row_meta    = dc.take<int4>(n * (mn + 1));
+        b->X.rd_capacity = align_up(std::max(cfg->max_sequence_size, 1), 4) + 8;
+        b->X.rd_node     = dc.take<uint8_t>(n * static_cast<int64_t>(b->X.rd_capacity) * S);
+        b->d_timers      = dc.take<unsigned long long>(n * 8);
+        b->X.timers      = nullptr;
+        b->X.pool_bytes  = b->score32 ? 54 * 1024 : 24 * 1024;
         // everything that is left is the score pool (allocate_block.hpp:227-239)
         dc.off                 = align_up64(dc.off, 256);
         P.scores               = b->d_block + dc.off;
@@ -471,6 +527,14 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     }
     cudaEventCreate(&b->ev0);
     cudaEventCreate(&b->ev1);
+    {
+        const char* k = std::getenv("GWB200_POA_KERNEL"); // development A/B switch: "v1" selects the first-generation kernel
+        b->use_v2     = !(k && std::string(k) == "v1");
+        if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536)
+            b->use_v2 = false; // wider static bands / longer reads than the v2 kernel packs: first-generation kernel
+        const char* nwv = std::getenv("GWB200_POA_WARPS"); // development switch: warps per window (1, 2 or 4)
+        b->nw_override  = nwv ? std::atoi(nwv) : 0;
+    }
     gwb200_poa_batch_reset(b);
     *out = b;
     return 0;
@@ -892,6 +956,32 @@ float gwb200_poa_batch_last_kernel_ms(gwb200_poa_batch* b)
         return -1.f;
     }
     return ms;
+}
+
+int gwb200_poa_batch_enable_timers(gwb200_poa_batch* b, int32_t on)
+{
+    if (!b)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null batch");
+    b->timers_on = on != 0;
+    return 0;
+}
+
+int gwb200_poa_batch_get_timers(gwb200_poa_batch* b, uint64_t* out8)
+{
+    if (!b || !out8)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(b->device_id);
+    for (int k = 0; k < 8; k++)
+        out8[k] = 0;
+    if (!b->launched || !b->timers_on || b->poa_count == 0)
+        return 0;
+    std::vector<unsigned long long> h(static_cast<size_t>(b->poa_count) * 8);
+    GWB200_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    GWB200_CUDA_TRY(cudaMemcpy(h.data(), b->d_timers, h.size() * 8, cudaMemcpyDeviceToHost));
+    for (int32_t w = 0; w < b->poa_count; w++)
+        for (int k = 0; k < 8; k++)
+            out8[k] += h[static_cast<size_t>(w) * 8 + k];
+    return 0;
 }
 
 int gwb200_device_fdividef(int32_t n, const float* a, const float* b, float* out)

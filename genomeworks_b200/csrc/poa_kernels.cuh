@@ -193,6 +193,13 @@ __device__ __forceinline__ void closure4(int32_t& s0, int32_t& s1, int32_t& s2, 
     s1 = max(s1, s0 + gap);
     s2 = max(s2, s1 + gap);
     s3 = max(s3, s2 + gap);
+    // Fast path (the common case: gaps are rare): if no lane's first cell is improved by the closed last cell of the lane to
+    // its left (lane 0: by the carry-in), nothing propagates and the lane-local values are final.
+    int32_t nb = __shfl_up_sync(kFull, s3, 1);
+    if (lane == 0)
+        nb = left;
+    if (__ballot_sync(kFull, nb + gap > s0) == 0u)
+        return;
     // t_l = max(left, max_{m<=l}(a3_m - 4*gap*(m+1))): inclusive prefix-max over lanes
     const int32_t g4 = 4 * gap;
     int32_t v        = s3 - g4 * (lane + 1);

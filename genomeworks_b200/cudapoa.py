@@ -228,6 +228,15 @@ class CudaPoaBatch:
     def last_kernel_ms(self):
         return float(lib().gwb200_poa_batch_last_kernel_ms(self._h))
 
+    def enable_timers(self, on=True):
+        check(lib().gwb200_poa_batch_enable_timers(self._h, C.c_int32(1 if on else 0)))
+
+    def get_timers(self):
+        """Per-phase cycle counters summed over windows: DP rows, end cell, traceback, add-alignment, topsort, consensus/MSA."""
+        out = np.zeros(8, dtype=np.uint64)
+        check(lib().gwb200_poa_batch_get_timers(self._h, out.ctypes.data))
+        return dict(zip(["dp_rows", "end_cell", "traceback", "add_alignment", "topsort", "consensus"], [int(x) for x in out[:6]]))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().gwb200_poa_batch_destroy(self._h)

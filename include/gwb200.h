@@ -161,6 +161,10 @@ int gwb200_poa_batch_reset(gwb200_poa_batch* batch);
  * launch measured with CUDA events on the batch's stream (ms; requires gwb200_poa_batch_sync first). */
 int64_t gwb200_poa_batch_last_cells(gwb200_poa_batch* batch);
 float gwb200_poa_batch_last_kernel_ms(gwb200_poa_batch* batch);
+/* Optional per-phase cycle counters of the POA kernel (development / profiling aid): enable before generate, read after
+ * sync. out8[0..5] = DP rows, end-cell search, traceback, add-alignment, topological sort, consensus/MSA; summed over windows. */
+int gwb200_poa_batch_enable_timers(gwb200_poa_batch* batch, int32_t on);
+int gwb200_poa_batch_get_timers(gwb200_poa_batch* batch, uint64_t* out8);
 /* sizeof(ScoreT) chosen for this batch (2 or 4), cudapoa_limits.hpp:34-44. */
 int32_t gwb200_poa_batch_score_bytes(const gwb200_poa_batch* batch);
 

@@ -1,4 +1,5 @@
-"""Quick C2 timing: ours vs the reference kernels on the same GPU (development aid; bench.py is the contract)."""
+"""Development aid: time a POA config (ours, optional v1 A/B via GWB200_POA_KERNEL=v1) and print per-phase cycle shares.
+usage: quick_poa.py {c2|c3} [n_windows] [--ref]"""
 import os
 import sys
 import time
@@ -10,21 +11,39 @@ import numpy as np
 from genomeworks_b200 import cudapoa, synth
 import ref_lib
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-win_nseq, seq_len, data = synth.poa_windows(n, 1000, 16, 20, 10, 10, seed0=1000, max_read_len=1024)
-cfg = cudapoa.make_config(1024, 16, 256, "static_band")
-b = cudapoa.CudaPoaBatch(16, 1024, 16 << 30, config=cfg)
+which = sys.argv[1] if len(sys.argv) > 1 else "c2"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else (1024 if which == "c2" else 148)
+if which == "c2":
+    win_nseq, seq_len, data = synth.poa_windows(n, 1000, 16, 20, 10, 10, seed0=1000, max_read_len=1024)
+    cfg = cudapoa.make_config(1024, 16, 256, "static_band")
+    mem = 16 << 30
+    ref_args = (1024, 16, 256, 1)
+    factor = 2.0
+else:
+    win_nseq, seq_len, data = synth.poa_windows(n, 10000, 32, 200, 100, 100, seed0=1000, max_read_len=10240)
+    cfg = cudapoa.make_config(10240, 32, 256, "adaptive_band", adaptive_storage_factor=6.0)
+    mem = int(n * 215e6) + (2 << 30)
+    ref_args = (10240, 32, 256, 2)
+    factor = 6.0
+b = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, config=cfg)
+print("kernel", os.environ.get("GWB200_POA_KERNEL", "v2"), "max_poas", b.max_poas, flush=True)
 for it in range(3):
     b.reset()
-    t0 = time.time()
     b.add_poa_groups_flat(win_nseq, seq_len, data)
+    b.enable_timers(it == 2)
     t1 = time.time()
     b.generate_poa()
     c, cov, lens, st = b.get_consensus_arrays()
     t2 = time.time()
-    print("ours: add %.1f ms, generate+get %.1f ms, kernel %.2f ms, cells %.3e, ok=%d" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, b.last_kernel_ms(),
-                                                                                      b.last_cells(), int((st == 0).sum())), flush=True)
-if ref_lib.have_gwref():
-    for it in range(2):
-        r = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 256, 1)
-        print("ref : total %.1f ms, generate+get %.1f ms, batches %d" % (r["timings"][0], r["timings"][1], r["timings"][2]), flush=True)
+    print("ours: generate+get %.1f ms, kernel %.2f ms, cells %.3e, ok=%d  -> %.0f windows/s" % ((t2 - t1) * 1e3, b.last_kernel_ms(), b.last_cells(),
+                                                                                             int((st == 0).sum()), n / (b.last_kernel_ms() / 1e3)), flush=True)
+tm = b.get_timers()
+tot = max(1, sum(tm.values()))
+print("phase shares:", {k: "%.1f%%" % (100.0 * v / tot) for k, v in tm.items()}, "cycles/window %.3e" % (tot / n), flush=True)
+ours = [bytes(c[i, :lens[i]]).decode() for i in range(n)]
+b.close()
+if "--ref" in sys.argv and ref_lib.have_gwref():
+    r = ref_lib.ref_poa_run(win_nseq, seq_len, data, *ref_args, adaptive_storage_factor=factor, mem_fraction=0.5, max_windows_per_batch=n)
+    r = ref_lib.ref_poa_run(win_nseq, seq_len, data, *ref_args, adaptive_storage_factor=factor, mem_fraction=0.5, max_windows_per_batch=n)
+    print("ref : generate+get %.1f ms -> %.0f windows/s; identical=%s" % (r["timings"][1], n / (r["timings"][1] / 1e3),
+                                                                        r["consensus"] == ours and list(r["status"]) == list(st)), flush=True)
