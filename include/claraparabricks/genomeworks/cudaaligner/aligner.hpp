@@ -1,0 +1,213 @@
+// gw-b200: cudaaligner::Aligner / FixedBandAligner / create_aligner with the reference's signatures
+// (cudaaligner/include/claraparabricks/genomeworks/cudaaligner/aligner.hpp:41-219), as a header-only adapter over the
+// C ABI of libgwb200.so. Both factory families are served by the banded Myers engine: the FixedBand overloads directly;
+// the deprecated (max_query, max_target, max_alignments) overloads with a bandwidth covering the whole query (full Myers,
+// exact; the reference uses AlignerGlobalHirschbergMyers there, cudaaligner/src/aligner.cpp:31-74).
+#pragma once
+
+#include "alignment.hpp"
+#include "../utils/allocator.hpp"
+
+#include <cuda_runtime_api.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace claraparabricks
+{
+namespace genomeworks
+{
+namespace cudaaligner
+{
+
+/// Device-resident results (aligner.hpp:62-72); pointers are borrowed until reset() / destruction.
+struct DeviceAlignmentsPtrs
+{
+    const int8_t* cigar_operations;
+    const int32_t* cigar_runlengths;
+    const int32_t* cigar_offsets;
+    const uint32_t* metadata; ///< bit 31: is_optimal, bits 26-0: index of the alignment in insertion order
+    int64_t total_length;
+    int32_t n_alignments;
+    static constexpr uint32_t index_mask = (1u << 27) - 1;
+};
+
+class Aligner
+{
+public:
+    virtual ~Aligner()                   = default;
+    virtual StatusType align_all()       = 0;
+    virtual StatusType sync_alignments() = 0;
+    virtual StatusType add_alignment(const char* query, int32_t query_length, const char* target, int32_t target_length,
+                                     bool reverse_complement_query = false, bool reverse_complement_target = false) = 0;
+    virtual const std::vector<std::shared_ptr<Alignment>>& get_alignments() const                                      = 0;
+    virtual DeviceAlignmentsPtrs get_alignments_device() const                                                         = 0;
+    virtual void reset()                                                                                               = 0;
+    virtual void free_temporary_device_buffers()                                                                       = 0;
+    virtual int32_t num_alignments() const                                                                             = 0;
+    virtual cudaStream_t get_stream() const                                                                            = 0;
+    virtual int32_t get_device() const                                                                                 = 0;
+    virtual DefaultDeviceAllocator get_device_allocator() const                                                        = 0;
+};
+
+class FixedBandAligner : public Aligner
+{
+public:
+    virtual void reset_max_bandwidth(int32_t max_bandwidth) = 0;
+    using Aligner::add_alignment;
+    virtual StatusType add_alignment(int32_t max_bandwidth, const char* query, int32_t query_length, const char* target, int32_t target_length,
+                                     bool reverse_complement_query = false, bool reverse_complement_target = false) = 0;
+};
+
+namespace detail
+{
+class AlignerB200 : public FixedBandAligner
+{
+public:
+    AlignerB200(int32_t max_bandwidth, cudaStream_t stream, int32_t device_id, int64_t max_device_memory, int32_t max_query = -1,
+                int32_t max_target = -1, int32_t max_alignments = -1)
+        : stream_(stream)
+        , device_(device_id)
+        , mem_(max_device_memory)
+        , max_query_(max_query)
+        , max_target_(max_target)
+        , max_alignments_(max_alignments)
+    {
+        check(gwb200_aligner_create(&h_, max_bandwidth, stream, device_id, max_device_memory));
+    }
+    ~AlignerB200() override { gwb200_aligner_destroy(h_); }
+    AlignerB200(const AlignerB200&) = delete;
+    AlignerB200& operator=(const AlignerB200&) = delete;
+
+    StatusType add_alignment(const char* query, int32_t query_length, const char* target, int32_t target_length, bool rc_q = false,
+                             bool rc_t = false) override
+    {
+        return add_alignment(0, query, query_length, target, target_length, rc_q, rc_t);
+    }
+    StatusType add_alignment(int32_t max_bandwidth, const char* query, int32_t query_length, const char* target, int32_t target_length,
+                             bool rc_q = false, bool rc_t = false) override
+    {
+        if (max_query_ >= 0 && (query_length > max_query_ || target_length > max_target_))
+            return StatusType::exceeded_max_length; // AlignerGlobal::add_alignment, cudaaligner/src/aligner_global.cpp:50-86
+        if (max_alignments_ >= 0 && num_alignments() >= max_alignments_)
+            return StatusType::exceeded_max_alignments;
+        const int rc = check(gwb200_aligner_add_alignment(h_, max_bandwidth, query, query_length, target, target_length, rc_q ? 1 : 0, rc_t ? 1 : 0));
+        if (rc == success)
+            pending_.emplace_back(std::string(query, query + query_length), std::string(target, target + target_length));
+        return static_cast<StatusType>(rc);
+    }
+    StatusType align_all() override { return static_cast<StatusType>(check(gwb200_aligner_align_all(h_))); }
+    StatusType sync_alignments() override
+    {
+        const int rc = check(gwb200_aligner_sync_alignments(h_));
+        alignments_.clear();
+        for (size_t i = 0; i < pending_.size(); ++i)
+        {
+            int32_t st = 0, opt = 0, n = 0;
+            check(gwb200_aligner_result_info(h_, static_cast<int32_t>(i), &st, &opt, &n));
+            std::vector<int8_t> a(std::max(n, 1));
+            std::vector<int32_t> r(std::max(n, 1));
+            check(gwb200_aligner_result_runs(h_, static_cast<int32_t>(i), a.data(), r.data()));
+            a.resize(n);
+            r.resize(n);
+            auto al = std::make_shared<AlignmentB200>(std::move(pending_[i].first), std::move(pending_[i].second));
+            if (st == success)
+                al->set(StatusType::success, opt != 0, std::move(a), std::move(r));
+            alignments_.push_back(std::move(al));
+        }
+        pending_.clear();
+        return static_cast<StatusType>(rc);
+    }
+    const std::vector<std::shared_ptr<Alignment>>& get_alignments() const override { return alignments_; }
+    DeviceAlignmentsPtrs get_alignments_device() const override
+    {
+        DeviceAlignmentsPtrs p{};
+        check(gwb200_aligner_get_alignments_device(h_, &p.cigar_operations, &p.cigar_runlengths, &p.cigar_offsets, &p.metadata, &p.total_length,
+                                                   &p.n_alignments));
+        return p;
+    }
+    void reset() override
+    {
+        check(gwb200_aligner_reset(h_));
+        pending_.clear();
+        alignments_.clear();
+    }
+    void reset_max_bandwidth(int32_t max_bandwidth) override
+    {
+        check(gwb200_aligner_reset_max_bandwidth(h_, max_bandwidth));
+        pending_.clear();
+        alignments_.clear();
+    }
+    void free_temporary_device_buffers() override { check(gwb200_aligner_free_temporary_device_buffers(h_)); }
+    int32_t num_alignments() const override { return gwb200_aligner_num_alignments(h_); }
+    cudaStream_t get_stream() const override { return stream_; }
+    int32_t get_device() const override { return device_; }
+    DefaultDeviceAllocator get_device_allocator() const override { return DefaultDeviceAllocator(mem_, stream_); }
+
+private:
+    gwb200_aligner* h_ = nullptr;
+    cudaStream_t stream_;
+    int32_t device_;
+    int64_t mem_;
+    int32_t max_query_, max_target_, max_alignments_;
+    std::vector<std::pair<std::string, std::string>> pending_;
+    std::vector<std::shared_ptr<Alignment>> alignments_;
+};
+
+inline int32_t covering_bandwidth(int32_t max_query_length, int32_t max_target_length)
+{
+    int32_t bw = std::max(std::max(max_query_length, max_target_length), 2);
+    if (bw % 32 == 1)
+        ++bw;
+    return bw;
+}
+} // namespace detail
+
+/// Deprecated factory (aligner.hpp:183): fixed maximum lengths / count.
+inline std::unique_ptr<Aligner> create_aligner(int32_t max_query_length, int32_t max_target_length, int32_t max_alignments, AlignmentType type,
+                                               DefaultDeviceAllocator allocator, cudaStream_t stream, int32_t device_id)
+{
+    if (type != AlignmentType::global_alignment)
+        throw std::runtime_error("Aligner for specified type not implemented yet.");
+    return std::unique_ptr<Aligner>(new detail::AlignerB200(detail::covering_bandwidth(max_query_length, max_target_length), stream, device_id,
+                                                            allocator.get_size_of_largest_free_memory_block(), max_query_length,
+                                                            max_target_length, max_alignments));
+}
+/// Deprecated factory (aligner.hpp:196).
+inline std::unique_ptr<Aligner> create_aligner(int32_t max_query_length, int32_t max_target_length, int32_t max_alignments, AlignmentType type,
+                                               cudaStream_t stream, int32_t device_id, int64_t max_device_memory_allocator_caching_size = -1)
+{
+    if (type != AlignmentType::global_alignment)
+        throw std::runtime_error("Aligner for specified type not implemented yet.");
+    if (max_device_memory_allocator_caching_size < -1)
+        throw std::invalid_argument("max_device_memory_allocator_caching_size has to be either -1 (=all available GPU memory) or greater or equal than 0.");
+    return std::unique_ptr<Aligner>(new detail::AlignerB200(detail::covering_bandwidth(max_query_length, max_target_length), stream, device_id,
+                                                            max_device_memory_allocator_caching_size, max_query_length, max_target_length,
+                                                            max_alignments));
+}
+/// FixedBand factory with allocator (aligner.hpp:208): max_device_memory == -1 => the allocator's largest free block.
+inline std::unique_ptr<FixedBandAligner> create_aligner(AlignmentType type, int32_t max_bandwidth, cudaStream_t stream, int32_t device_id,
+                                                        DefaultDeviceAllocator allocator, int64_t max_device_memory)
+{
+    if (type != AlignmentType::global_alignment)
+        throw std::runtime_error("Aligner for specified type not implemented yet.");
+    if (max_device_memory < -1)
+        throw std::invalid_argument("max_device_memory has to be either -1 (=all available GPU memory) or greater or equal than 0.");
+    if (max_device_memory == -1)
+        max_device_memory = allocator.get_size_of_largest_free_memory_block();
+    return std::unique_ptr<FixedBandAligner>(new detail::AlignerB200(max_bandwidth, stream, device_id, max_device_memory));
+}
+/// FixedBand factory (aligner.hpp:219).
+inline std::unique_ptr<FixedBandAligner> create_aligner(AlignmentType type, int32_t max_bandwidth, cudaStream_t stream, int32_t device_id,
+                                                        int64_t max_device_memory = -1)
+{
+    if (type != AlignmentType::global_alignment)
+        throw std::runtime_error("Aligner for specified type not implemented yet.");
+    return std::unique_ptr<FixedBandAligner>(new detail::AlignerB200(max_bandwidth, stream, device_id, max_device_memory));
+}
+
+} // namespace cudaaligner
+} // namespace genomeworks
+} // namespace claraparabricks
