@@ -245,7 +245,9 @@ def main():
     n_win = args.windows or wp["windows"]
     if args.workload == "c3" and not args.windows:
         # one full batch per GPU: as many windows as the batch holds, rounded to a multiple of the SM count
-        n_win = batch.max_poas // 148 * 148 if batch.max_poas >= 148 else batch.max_poas
+        # and capped at what the device keeps resident at once (one wave)
+        n_win = min(batch.max_poas, max(batch.resident_windows, 148))
+        n_win = n_win // 148 * 148 if n_win >= 148 else n_win
     if batch.max_poas < n_win:
         raise SystemExit("batch capacity %d < requested windows %d" % (batch.max_poas, n_win))
     # every rank owns its own windows (seeds disjoint across ranks): weak scaling, no data-path collective

@@ -50,7 +50,7 @@ def lib():
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.gwb200_poa_batch_add_groups_flat.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.POINTER(C.c_int32)]
-    for name in ("total_poas", "max_poas", "generate", "upload", "launch", "sync", "id", "reset", "score_bytes"):
+    for name in ("total_poas", "max_poas", "generate", "upload", "launch", "sync", "id", "reset", "score_bytes", "resident_windows"):
         getattr(L, "gwb200_poa_batch_" + name).argtypes = [C.c_void_p]
     L.gwb200_poa_batch_get_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gwb200_poa_batch_get_msa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

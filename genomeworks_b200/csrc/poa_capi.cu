@@ -156,54 +156,110 @@ Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz,
     return s;
 }
 
-template <typename ScoreT, typename SizeT>
-void launch_typed(gwb200_poa_batch* b)
+// Kernel selection for a batch: warps per window and band chunks per warp.
+struct V2Choice
 {
-    dim3 grid(b->poa_count), block(32);
+    int32_t nw, maxc;
+};
+V2Choice choose_v2(const gwb200_poa_batch* b)
+{
+    // warps per window: one per 128-column band chunk, at most 4; chunks per warp bounded by the widest band the mode can
+    // reach (adaptive bands grow up to 1536 = 12 chunks)
+    const bool adaptive   = b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND && b->cfg.alignment_band_width < kMaxAdaptiveBW;
+    const int32_t nchunks = adaptive ? kMaxAdaptiveBW / 128 : std::max(1, b->cfg.alignment_band_width / 128);
+    // measured on B200 (profiles/): up to 2 chunks one warp is fastest (no CTA barriers); wider bands use 4 warps
+    int32_t nw = nchunks >= 3 ? 4 : 1;
+    if (b->cfg.band_mode == GWB200_POA_FULL_BAND)
+        nw = 1;
+    if (b->nw_override > 0 && !adaptive && nchunks <= 4)
+        nw = b->nw_override; // development switch
+    if (nw == 1 && nchunks == 2)
+        return {1, 2};
+    if (nchunks > 4 || nw < std::min(nchunks, 4))
+        return {4, 3};
+    if (nw == 4)
+        return {4, 1};
+    if (nw == 2)
+        return {2, 1};
+    return {1, 1};
+}
+
+// action 0: launch; action 1: return resident CTAs per SM (occupancy) for the chosen kernel
+template <typename ScoreT, typename SizeT, int32_t NW, int32_t MAXC>
+int32_t v2_action(gwb200_poa_batch* b, int action)
+{
+    auto kfn           = poa_window_kernel_v2<ScoreT, SizeT, NW, MAXC>;
+    const int32_t smem = b->X.pool_bytes;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (action == 1)
+    {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 32 * NW, smem) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        return nb;
+    }
+    kfn<<<b->poa_count, 32 * NW, smem, b->stream>>>(b->P, b->X);
+    return 0;
+}
+
+template <typename ScoreT, typename SizeT>
+int32_t typed_action(gwb200_poa_batch* b, int action)
+{
     if (b->use_v2)
     {
-        b->X.timers = b->timers_on ? b->d_timers : nullptr;
-        if (b->timers_on)
-            cudaMemsetAsync(b->d_timers, 0, sizeof(unsigned long long) * 8 * b->poa_count, b->stream);
-        // warps per window: one per 128-column band chunk, at most 4; chunks per warp bounded by the widest band the mode can
-        // reach (adaptive bands grow up to 1536 = 12 chunks)
-        const bool adaptive   = b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND && b->cfg.alignment_band_width < kMaxAdaptiveBW;
-        const int32_t nchunks = adaptive ? kMaxAdaptiveBW / 128 : std::max(1, b->cfg.alignment_band_width / 128);
-        // measured on B200 (profiles/): up to 2 chunks one warp is fastest (no CTA barriers); wider bands use 4 warps
-        int32_t nw            = nchunks >= 3 ? 4 : 1;
-        if (b->cfg.band_mode == GWB200_POA_FULL_BAND)
-            nw = 1;
-        if (b->nw_override > 0 && !adaptive && nchunks <= 4)
-            nw = b->nw_override; // development switch; MAXC = 1 kernels need nw >= nchunks, checked below
-        const int32_t smem = b->X.pool_bytes;
-#define GWB200_LAUNCH_V2(NWv, MAXCv)                                                                          \
-    do                                                                                                        \
-    {                                                                                                         \
-        auto kfn = poa_window_kernel_v2<ScoreT, SizeT, NWv, MAXCv>;                                           \
-        if (smem > 48 * 1024)                                                                                 \
-            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                     \
-        kfn<<<grid, 32 * NWv, smem, b->stream>>>(b->P, b->X);                                                  \
-    } while (0)
-        if (nw == 1 && nchunks == 2)
-            GWB200_LAUNCH_V2(1, 2);
-        else if (nchunks > 4 || nw < std::min(nchunks, 4))
-            GWB200_LAUNCH_V2(4, 3);
-        else if (nw == 4)
-            GWB200_LAUNCH_V2(4, 1);
-        else if (nw == 2)
-            GWB200_LAUNCH_V2(2, 1);
+        if (action == 0)
+        {
+            b->X.timers = b->timers_on ? b->d_timers : nullptr;
+            if (b->timers_on)
+                cudaMemsetAsync(b->d_timers, 0, sizeof(unsigned long long) * 8 * b->poa_count, b->stream);
+        }
+        const V2Choice ch = choose_v2(b);
+        int32_t r;
+        if (ch.nw == 1 && ch.maxc == 2)
+            r = v2_action<ScoreT, SizeT, 1, 2>(b, action);
+        else if (ch.nw == 4 && ch.maxc == 3)
+            r = v2_action<ScoreT, SizeT, 4, 3>(b, action);
+        else if (ch.nw == 4)
+            r = v2_action<ScoreT, SizeT, 4, 1>(b, action);
+        else if (ch.nw == 2)
+            r = v2_action<ScoreT, SizeT, 2, 1>(b, action);
         else
-            GWB200_LAUNCH_V2(1, 1);
-#undef GWB200_LAUNCH_V2
+            r = v2_action<ScoreT, SizeT, 1, 1>(b, action);
+        if (action == 0)
+            count_launch();
+        return r;
     }
-    else
+    if (action == 1)
     {
-        if (b->msa)
-            poa_window_kernel<ScoreT, SizeT, true><<<grid, block, 0, b->stream>>>(b->P);
-        else
-            poa_window_kernel<ScoreT, SizeT, false><<<grid, block, 0, b->stream>>>(b->P);
+        int nb = 0;
+        auto kfn = poa_window_kernel<ScoreT, SizeT, false>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 32, 0) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        return nb;
     }
+    dim3 grid(b->poa_count), block(32);
+    if (b->msa)
+        poa_window_kernel<ScoreT, SizeT, true><<<grid, block, 0, b->stream>>>(b->P);
+    else
+        poa_window_kernel<ScoreT, SizeT, false><<<grid, block, 0, b->stream>>>(b->P);
     count_launch();
+    return 0;
+}
+
+int32_t batch_action(gwb200_poa_batch* b, int action)
+{
+    if (!b->score32 && !b->size32)
+        return typed_action<int16_t, int16_t>(b, action);
+    if (b->score32 && !b->size32)
+        return typed_action<int32_t, int16_t>(b, action);
+    return typed_action<int32_t, int32_t>(b, action);
 }
 
 int validate_config(const gwb200_poa_config& c)
@@ -530,8 +586,14 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     {
         const char* k = std::getenv("GWB200_POA_KERNEL"); // development A/B switch: "v1" selects the first-generation kernel
         b->use_v2     = !(k && std::string(k) == "v1");
-        if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536)
-            b->use_v2 = false; // wider static bands / longer reads than the v2 kernel packs: first-generation kernel
+        {
+            // the v2 kernel stages the read and at least two score rows in its shared-memory pool and packs band starts in 14 bits
+            const int64_t max_bw  = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
+            const int64_t pool    = b->score32 ? 54 * 1024 : 24 * 1024;
+            const int64_t need    = (b->cfg.max_sequence_size + max_bw + 24) + 2 * (max_bw + 8) * b->score_bytes;
+            if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || need > pool)
+                b->use_v2 = false; // first-generation kernel
+        }
         const char* nwv = std::getenv("GWB200_POA_WARPS"); // development switch: warps per window (1, 2 or 4)
         b->nw_override  = nwv ? std::atoi(nwv) : 0;
     }
@@ -733,12 +795,7 @@ int gwb200_poa_batch_launch(gwb200_poa_batch* b)
     DeviceGuard guard(b->device_id);
     b->P.n_windows = b->poa_count;
     GWB200_CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
-    if (!b->score32 && !b->size32)
-        launch_typed<int16_t, int16_t>(b);
-    else if (b->score32 && !b->size32)
-        launch_typed<int32_t, int16_t>(b);
-    else
-        launch_typed<int32_t, int32_t>(b);
+    batch_action(b, 0);
     GWB200_CUDA_TRY(cudaPeekAtLastError());
     GWB200_CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
     b->launched        = true;
@@ -956,6 +1013,16 @@ float gwb200_poa_batch_last_kernel_ms(gwb200_poa_batch* b)
         return -1.f;
     }
     return ms;
+}
+
+int32_t gwb200_poa_batch_resident_windows(gwb200_poa_batch* b)
+{
+    if (!b)
+        return 0;
+    DeviceGuard guard(b->device_id);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device_id);
+    return sms * batch_action(b, 1);
 }
 
 int gwb200_poa_batch_enable_timers(gwb200_poa_batch* b, int32_t on)

@@ -125,14 +125,31 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
     const int32_t stride = B.stride;
     const int32_t nchunks = band_width / 128;
 
-    // shared-memory ring of the most recent score rows: row r lives in slot r % R
-    ScoreT* ring        = reinterpret_cast<ScoreT*>(pool);
-    int32_t R           = pool_bytes / (stride * static_cast<int32_t>(sizeof(ScoreT)));
-    R                   = min(R, 64);
-    const bool use_ring = R >= 2;
+    // ---- shared memory during the DP phase: [ staged read | ring of the most recent score rows (row r in slot r % R) ]
+    const int32_t sread_bytes = (read_length + band_width + 8 + 15) & ~15;
+    uint8_t* sread            = pool;
+    ScoreT* ring              = reinterpret_cast<ScoreT*>(pool + sread_bytes);
+    int32_t R                 = (pool_bytes - sread_bytes) / (stride * static_cast<int32_t>(sizeof(ScoreT)));
+    R                         = min(R, 64);
+    const bool use_ring       = R >= 2;
     if (R < 1)
         R = 1;
-
+    {
+        // stage the read (4-byte aligned in the packed input); bytes past its end are zero: they only ever reach cells with
+        // column > read_length, which never influence columns <= read_length
+        const uint32_t* rd32 = reinterpret_cast<const uint32_t*>(read);
+        uint32_t* sr32       = reinterpret_cast<uint32_t*>(sread);
+        const int32_t nfull  = read_length >> 2;
+        for (int32_t i = threadIdx.x; i < sread_bytes / 4; i += 32 * NW)
+        {
+            uint32_t v = 0;
+            if (i < nfull)
+                v = __ldg(rd32 + i);
+            else if (i == nfull && (read_length & 3))
+                v = __ldg(rd32 + i) & ((1u << (8 * (read_length & 3))) - 1u);
+            sr32[i] = v;
+        }
+    }
     for (int32_t j = threadIdx.x; j < stride; j += 32 * NW)
     {
         const ScoreT v = static_cast<ScoreT>(j * gap);
@@ -142,9 +159,9 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
     }
     __syncthreads();
 
-    // ---- metadata of the first group of rows (blocking); later groups are fetched one group ahead. Every warp keeps its
-    // own copy (the loads hit L1), warp 0 also writes it to row_meta for the traceback.
-    int32_t nx_node = 0, nx_misc = 0, nx_p0 = 0, nx_p1 = 0;
+    // ---- per-row metadata: fetched 32 rows at a time by the lanes, one group ahead of its use (every warp keeps its own
+    // copy, the loads hit L1); warp 0 also writes it to row_meta for the end-cell search and the traceback.
+    int32_t nx_node = 0, nx_misc = 0, nx_p0 = 0, nx_p1 = 0, nx_bs = 0, nx_bsp0 = 0;
     {
         const int32_t row = 1 + lane;
         if (row <= graph_count)
@@ -155,17 +172,20 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
             nx_misc            = static_cast<int32_t>(g.nodes[node]) | (pc << 8) | ((g.out_cnt[node] == 0 ? 1 : 0) << 16);
             nx_p0              = pc > 0 ? static_cast<int32_t>(g.pos[g.in_edge(node, 0)]) + 1 : 0;
             nx_p1              = pc > 1 ? static_cast<int32_t>(g.pos[g.in_edge(node, 1)]) + 1 : 0;
+            nx_bs              = B.start(row);
+            nx_bsp0            = B.start(nx_p0);
         }
     }
     int32_t ring_slot = 0; // slot of the current row = row % R, maintained incrementally
+    const int32_t G   = 128 * gap;
 
     for (int32_t r0 = 1; r0 <= graph_count; r0 += 32)
     {
-        const int32_t cur_node = nx_node, cur_misc = nx_misc, cur_p0 = nx_p0, cur_p1 = nx_p1;
+        const int32_t cur_node = nx_node, cur_misc = nx_misc, cur_p0 = nx_p0, cur_p1 = nx_p1, cur_bs = nx_bs, cur_bsp0 = nx_bsp0;
         const int32_t nrows    = min(32, graph_count - r0 + 1);
         const bool have_next   = r0 + 32 <= graph_count;
         if (warp == 0 && lane < nrows)
-            row_meta[r0 + lane] = make_int4(cur_node, cur_p0, cur_p1, cur_misc | ((B.start(r0 + lane) >> 2) << 17));
+            row_meta[r0 + lane] = make_int4(cur_node, cur_p0, cur_p1, cur_misc | ((cur_bs >> 2) << 17));
         const int32_t nrow = r0 + 32 + lane;
         const bool nvalid  = have_next && nrow <= graph_count;
         int32_t t_node = 0, t_base = 0, t_pc = 0, t_oc = 1, t_e0 = 0, t_e1 = 0;
@@ -198,129 +218,195 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                         nx_misc = t_base | (t_pc << 8) | ((t_oc == 0 ? 1 : 0) << 16);
                         nx_p0   = t_pc > 0 ? static_cast<int32_t>(g.pos[t_e0]) + 1 : 0;
                         nx_p1   = t_pc > 1 ? static_cast<int32_t>(g.pos[t_e1]) + 1 : 0;
+                        nx_bs   = B.start(nrow);
+                        nx_bsp0 = B.start(nx_p0);
                     }
                 }
             }
-            const int32_t row     = r0 + k;
-            const int32_t node_id = __shfl_sync(kFull, cur_node, k);
-            const int32_t misc    = __shfl_sync(kFull, cur_misc, k);
-            const int32_t p0      = __shfl_sync(kFull, cur_p0, k);
-            const int32_t p1      = __shfl_sync(kFull, cur_p1, k);
-            const int32_t base    = misc & 0xff;
-            const int32_t pc      = (misc >> 8) & 0xff;
-            const int32_t bs      = B.start(row);
-            ring_slot             = (ring_slot + 1 == R) ? 0 : ring_slot + 1;
-            ScoreT* rowp          = B.row_ptr(row);
-            ScoreT* srow          = ring + ring_slot * stride;
-            int32_t* xchg         = s_xchg + (row & 1) * 16; // chunk-out values, double buffered by row parity
+            const int32_t row  = r0 + k;
+            const int32_t misc = __shfl_sync(kFull, cur_misc, k);
+            const int32_t p0   = __shfl_sync(kFull, cur_p0, k);
+            const int32_t bs   = __shfl_sync(kFull, cur_bs, k);
+            const int32_t bsp0 = __shfl_sync(kFull, cur_bsp0, k);
+            const int32_t base = misc & 0xff;
+            const int32_t pc   = (misc >> 8) & 0xff;
+            ring_slot          = (ring_slot + 1 == R) ? 0 : ring_slot + 1;
+            ScoreT* rowp       = B.row_ptr(row);
+            ScoreT* srow       = ring + ring_slot * stride;
+            int32_t* xchg      = s_xchg + (row & 1) * 16; // chunk-out values, double buffered by row parity
 
-            // row p is in the ring iff row - p < R; its slot is (ring_slot - (row - p)) mod R
-            auto pred_row_ptr = [&](int32_t p) -> const ScoreT* {
-                const int32_t d = row - p;
-                if (use_ring && d < R)
-                {
-                    int32_t sl = ring_slot - d;
-                    if (sl < 0)
-                        sl += R;
-                    return ring + sl * stride;
-                }
-                return B.row_ptr(p);
-            };
-
-            int32_t first = 0;
-            if (pc != 0)
-            {
-                if (bs > kCPT && pc == 1)
-                {
-                    first = kMin + gap;
-                }
-                else
-                {
-                    int32_t penalty = max(kMin, static_cast<int32_t>(pred_row_ptr(p0)[0]));
-                    if (pc > 1)
-                        penalty = max(penalty, static_cast<int32_t>(pred_row_ptr(p1)[0]));
-                    for (int32_t p = 2; p < pc; p++)
-                    {
-                        const int32_t pi = static_cast<int32_t>(g.pos[g.in_edge(node_id, p)]) + 1;
-                        penalty          = max(penalty, static_cast<int32_t>(pred_row_ptr(pi)[0]));
-                    }
-                    first = penalty + gap;
-                }
-            }
-            const int32_t local0 = (bs == 0) ? (pc == 0 ? gap : first) : kMin;
-            const int32_t carry0 = (pc == 0) ? 0 : first; // first_element_prev_score stays 0 for source nodes
-
-            // predecessor row pointers / band starts of the first two predecessors are chunk independent
-            const ScoreT* pp0   = pred_row_ptr(p0);
-            const int32_t bsp0  = B.start(p0);
-            const int32_t bep0  = min(bsp0 + band_width - kCPT, max_column);
-            const ScoreT* pp1   = pp0;
-            int32_t bsp1 = 0, bep1 = -1;
-            if (pc > 1)
-            {
-                pp1  = pred_row_ptr(p1);
-                bsp1 = B.start(p1);
-                bep1 = min(bsp1 + band_width - kCPT, max_column);
-            }
-
-            // ---- phase 1: chunk-local values (no carry-in) for this warp's chunks
+            int32_t local0, carry0;
             int32_t a0[kMaxChunksPerWarp], a1[kMaxChunksPerWarp], a2[kMaxChunksPerWarp], a3[kMaxChunksPerWarp];
-#pragma unroll
-            for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
+            const int32_t d0 = row - p0;
+            int32_t p1       = 0;
+            bool ring_row    = use_ring && pc <= 2 && d0 < R;
+            if (ring_row && pc == 2)
             {
-                const int32_t c = warp + ci * NW;
-                if (c < nchunks)
+                p1       = __shfl_sync(kFull, cur_p1, k);
+                ring_row = (row - p1) < R;
+            }
+            if (ring_row)
+            {
+                // ---- common case: at most two predecessors, both still in the shared-memory ring
+                int32_t sl0 = ring_slot - d0;
+                if (sl0 < 0)
+                    sl0 += R;
+                const ScoreT* prow0 = ring + sl0 * stride;
+                const int32_t bep0  = min(bsp0 + band_width - kCPT, max_column);
+                const ScoreT* prow1 = prow0;
+                int32_t bsp1 = 0, bep1 = -1;
+                if (pc == 2)
                 {
-                    const int32_t read_pos = bs + c * 128 + 4 * lane;
-                    const uint32_t rd4     = __ldg(reinterpret_cast<const uint32_t*>(read + read_pos));
-                    const int32_t q0       = (base == static_cast<int32_t>(rd4 & 0xff)) ? match : mismatch;
-                    const int32_t q1       = (base == static_cast<int32_t>((rd4 >> 8) & 0xff)) ? match : mismatch;
-                    const int32_t q2       = (base == static_cast<int32_t>((rd4 >> 16) & 0xff)) ? match : mismatch;
-                    const int32_t q3       = (base == static_cast<int32_t>(rd4 >> 24)) ? match : mismatch;
-                    int32_t s0 = kMin, s1 = kMin, s2 = kMin, s3 = kMin;
-                    if (!(read_pos > bep0 || read_pos < bsp0))
+                    int32_t sl1 = ring_slot - (row - p1);
+                    if (sl1 < 0)
+                        sl1 += R;
+                    prow1 = ring + sl1 * stride;
+                    bsp1  = B.start(p1);
+                    bep1  = min(bsp1 + band_width - kCPT, max_column);
+                }
+                int32_t first = 0;
+                if (pc != 0)
+                {
+                    if (bs > kCPT && pc == 1)
                     {
-                        int32_t b0, b1, b2, b3, b4;
-                        load5<ScoreT>(pp0 + (read_pos - bsp0), b0, b1, b2, b3, b4);
-                        s0 = static_cast<ScoreT>(max(b0 + q0, b1 + gap));
-                        s1 = static_cast<ScoreT>(max(b1 + q1, b2 + gap));
-                        s2 = static_cast<ScoreT>(max(b2 + q2, b3 + gap));
-                        s3 = static_cast<ScoreT>(max(b3 + q3, b4 + gap));
+                        first = kMin + gap;
                     }
-                    if (pc > 1)
+                    else
                     {
-                        if (!(read_pos > bep1 || read_pos < bsp1))
+                        int32_t penalty = max(kMin, static_cast<int32_t>(prow0[0]));
+                        if (pc == 2)
+                            penalty = max(penalty, static_cast<int32_t>(prow1[0]));
+                        first = penalty + gap;
+                    }
+                }
+                local0 = (bs == 0) ? (pc == 0 ? gap : first) : kMin;
+                carry0 = (pc == 0) ? 0 : first;
+#pragma unroll
+                for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
+                {
+                    const int32_t c = warp + ci * NW;
+                    if (c < nchunks)
+                    {
+                        const int32_t read_pos = bs + c * 128 + 4 * lane;
+                        const uint32_t rd4     = *reinterpret_cast<const uint32_t*>(sread + read_pos);
+                        const int32_t q0       = (base == static_cast<int32_t>(rd4 & 0xff)) ? match : mismatch;
+                        const int32_t q1       = (base == static_cast<int32_t>((rd4 >> 8) & 0xff)) ? match : mismatch;
+                        const int32_t q2       = (base == static_cast<int32_t>((rd4 >> 16) & 0xff)) ? match : mismatch;
+                        const int32_t q3       = (base == static_cast<int32_t>(rd4 >> 24)) ? match : mismatch;
+                        int32_t s0 = kMin, s1 = kMin, s2 = kMin, s3 = kMin;
+                        if (read_pos >= bsp0 && read_pos <= bep0)
                         {
                             int32_t b0, b1, b2, b3, b4;
-                            load5<ScoreT>(pp1 + (read_pos - bsp1), b0, b1, b2, b3, b4);
+                            load5<ScoreT>(prow0 + (read_pos - bsp0), b0, b1, b2, b3, b4);
+                            s0 = static_cast<ScoreT>(max(b0 + q0, b1 + gap));
+                            s1 = static_cast<ScoreT>(max(b1 + q1, b2 + gap));
+                            s2 = static_cast<ScoreT>(max(b2 + q2, b3 + gap));
+                            s3 = static_cast<ScoreT>(max(b3 + q3, b4 + gap));
+                        }
+                        if (read_pos >= bsp1 && read_pos <= bep1)
+                        {
+                            int32_t b0, b1, b2, b3, b4;
+                            load5<ScoreT>(prow1 + (read_pos - bsp1), b0, b1, b2, b3, b4);
                             s0 = max(s0, static_cast<int32_t>(static_cast<ScoreT>(max(b0 + q0, b1 + gap))));
                             s1 = max(s1, static_cast<int32_t>(static_cast<ScoreT>(max(b1 + q1, b2 + gap))));
                             s2 = max(s2, static_cast<int32_t>(static_cast<ScoreT>(max(b2 + q2, b3 + gap))));
                             s3 = max(s3, static_cast<int32_t>(static_cast<ScoreT>(max(b3 + q3, b4 + gap))));
                         }
-                        for (int32_t p = 2; p < pc; p++)
+                        closure4(s0, s1, s2, s3, kNegInf, gap, lane);
+                        a0[ci] = s0;
+                        a1[ci] = s1;
+                        a2[ci] = s2;
+                        a3[ci] = s3;
+                        if (lane == 31)
+                            xchg[c] = s3;
+                    }
+                }
+            }
+            else
+            {
+                // ---- general case: any number of predecessors, rows older than the ring come from global memory
+                const int32_t node_id = __shfl_sync(kFull, cur_node, k);
+                p1                    = __shfl_sync(kFull, cur_p1, k);
+                auto pred_row_ptr = [&](int32_t p) -> const ScoreT* {
+                    const int32_t d = row - p;
+                    if (use_ring && d < R)
+                    {
+                        int32_t sl = ring_slot - d;
+                        if (sl < 0)
+                            sl += R;
+                        return ring + sl * stride;
+                    }
+                    return B.row_ptr(p);
+                };
+                int32_t first = 0;
+                if (pc != 0)
+                {
+                    if (bs > kCPT && pc == 1)
+                    {
+                        first = kMin + gap;
+                    }
+                    else
+                    {
+                        int32_t penalty = kMin;
+                        for (int32_t p = 0; p < pc; p++)
                         {
-                            const int32_t pi  = static_cast<int32_t>(g.pos[g.in_edge(node_id, p)]) + 1;
+                            const int32_t pi = (p == 0) ? p0 : (p == 1 ? p1 : static_cast<int32_t>(g.pos[g.in_edge(node_id, p)]) + 1);
+                            penalty          = max(penalty, static_cast<int32_t>(pred_row_ptr(pi)[0]));
+                        }
+                        first = penalty + gap;
+                    }
+                }
+                local0 = (bs == 0) ? (pc == 0 ? gap : first) : kMin;
+                carry0 = (pc == 0) ? 0 : first;
+                for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
+                {
+                    const int32_t c = warp + ci * NW;
+                    if (c < nchunks)
+                    {
+                        const int32_t read_pos = bs + c * 128 + 4 * lane;
+                        const uint32_t rd4     = *reinterpret_cast<const uint32_t*>(sread + read_pos);
+                        const int32_t q0       = (base == static_cast<int32_t>(rd4 & 0xff)) ? match : mismatch;
+                        const int32_t q1       = (base == static_cast<int32_t>((rd4 >> 8) & 0xff)) ? match : mismatch;
+                        const int32_t q2       = (base == static_cast<int32_t>((rd4 >> 16) & 0xff)) ? match : mismatch;
+                        const int32_t q3       = (base == static_cast<int32_t>(rd4 >> 24)) ? match : mismatch;
+                        int32_t s0 = kMin, s1 = kMin, s2 = kMin, s3 = kMin;
+                        const int32_t np = max(pc, 1);
+                        for (int32_t p = 0; p < np; p++)
+                        {
+                            const int32_t pi  = (p == 0) ? p0 : (p == 1 ? p1 : static_cast<int32_t>(g.pos[g.in_edge(node_id, p)]) + 1);
                             const int32_t bsp = B.start(pi);
                             const int32_t bep = min(bsp + band_width - kCPT, max_column);
+                            int32_t t0 = kMin, t1 = kMin, t2 = kMin, t3 = kMin;
                             if (!(read_pos > bep || read_pos < bsp))
                             {
                                 int32_t b0, b1, b2, b3, b4;
                                 load5<ScoreT>(pred_row_ptr(pi) + (read_pos - bsp), b0, b1, b2, b3, b4);
-                                s0 = max(s0, static_cast<int32_t>(static_cast<ScoreT>(max(b0 + q0, b1 + gap))));
-                                s1 = max(s1, static_cast<int32_t>(static_cast<ScoreT>(max(b1 + q1, b2 + gap))));
-                                s2 = max(s2, static_cast<int32_t>(static_cast<ScoreT>(max(b2 + q2, b3 + gap))));
-                                s3 = max(s3, static_cast<int32_t>(static_cast<ScoreT>(max(b3 + q3, b4 + gap))));
+                                t0 = static_cast<ScoreT>(max(b0 + q0, b1 + gap));
+                                t1 = static_cast<ScoreT>(max(b1 + q1, b2 + gap));
+                                t2 = static_cast<ScoreT>(max(b2 + q2, b3 + gap));
+                                t3 = static_cast<ScoreT>(max(b3 + q3, b4 + gap));
+                            }
+                            s0 = (p == 0) ? t0 : max(s0, t0);
+                            s1 = (p == 0) ? t1 : max(s1, t1);
+                            s2 = (p == 0) ? t2 : max(s2, t2);
+                            s3 = (p == 0) ? t3 : max(s3, t3);
+                        }
+                        closure4(s0, s1, s2, s3, kNegInf, gap, lane);
+                        // kMaxChunksPerWarp is small: select the slot without dynamic register indexing
+#pragma unroll
+                        for (int32_t u = 0; u < kMaxChunksPerWarp; u++)
+                        {
+                            if (u == ci)
+                            {
+                                a0[u] = s0;
+                                a1[u] = s1;
+                                a2[u] = s2;
+                                a3[u] = s3;
                             }
                         }
+                        if (lane == 31)
+                            xchg[c] = s3;
                     }
-                    closure4(s0, s1, s2, s3, kNegInf, gap, lane);
-                    a0[ci] = s0;
-                    a1[ci] = s1;
-                    a2[ci] = s2;
-                    a3[ci] = s3;
-                    if (lane == 31)
-                        xchg[c] = s3;
                 }
             }
             if (NW > 1)
@@ -328,27 +414,36 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
             else
                 __syncwarp();
 
-            // ---- phase 2: carry into each chunk, final values, stores (HBM + ring)
-            int32_t cin   = carry0; // closed value of the cell left of chunk cc
-            int32_t cleft = local0; // what is stored in the column left of chunk cc's first cell
-            int32_t cc    = 0;
+            // ---- phase 2: carry into every chunk by a lane-wise max-plus scan over the chunk-out values, final values, stores
+            int32_t cin_lane;
+            {
+                int32_t v = (lane < nchunks) ? (xchg[lane] - (lane + 1) * G) : kNegInf;
+#pragma unroll
+                for (int32_t d = 1; d < 16; d <<= 1)
+                {
+                    const int32_t o = __shfl_up_sync(kFull, v, d);
+                    if (lane >= d)
+                        v = max(v, o);
+                }
+                int32_t excl = __shfl_up_sync(kFull, v, 1);
+                if (lane == 0)
+                    excl = kNegInf;
+                cin_lane = static_cast<ScoreT>(lane * G + max(carry0, excl)); // closed value of the cell left of chunk `lane`
+            }
 #pragma unroll
             for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
             {
                 const int32_t c = warp + ci * NW;
                 if (c < nchunks)
                 {
-                    for (; cc < c; cc++)
-                    {
-                        cin   = static_cast<ScoreT>(max(xchg[cc], cin + 128 * gap));
-                        cleft = cin;
-                    }
-                    const int32_t L = cin + 4 * gap * lane;
-                    int32_t s0 = static_cast<ScoreT>(max(a0[ci], L + gap));
-                    int32_t s1 = static_cast<ScoreT>(max(a1[ci], L + 2 * gap));
-                    int32_t s2 = static_cast<ScoreT>(max(a2[ci], L + 3 * gap));
-                    int32_t s3 = static_cast<ScoreT>(max(a3[ci], L + 4 * gap));
-                    int32_t left = __shfl_up_sync(kFull, s3, 1);
+                    const int32_t cin   = __shfl_sync(kFull, cin_lane, c);
+                    const int32_t cleft = (c == 0) ? local0 : cin;
+                    const int32_t L     = cin + 4 * gap * lane;
+                    const int32_t s0    = static_cast<ScoreT>(max(a0[ci], L + gap));
+                    const int32_t s1    = static_cast<ScoreT>(max(a1[ci], L + 2 * gap));
+                    const int32_t s2    = static_cast<ScoreT>(max(a2[ci], L + 3 * gap));
+                    const int32_t s3    = static_cast<ScoreT>(max(a3[ci], L + 4 * gap));
+                    int32_t left        = __shfl_up_sync(kFull, s3, 1);
                     if (lane == 0)
                         left = cleft;
                     Vec4<ScoreT> out;

@@ -219,6 +219,10 @@ class CudaPoaBatch:
         return lib().gwb200_poa_batch_max_poas(self._h)
 
     @property
+    def resident_windows(self):
+        return lib().gwb200_poa_batch_resident_windows(self._h)
+
+    @property
     def score_bytes(self):
         return lib().gwb200_poa_batch_score_bytes(self._h)
 

@@ -165,6 +165,9 @@ float gwb200_poa_batch_last_kernel_ms(gwb200_poa_batch* batch);
  * sync. out8[0..5] = DP rows, end-cell search, traceback, add-alignment, topological sort, consensus/MSA; summed over windows. */
 int gwb200_poa_batch_enable_timers(gwb200_poa_batch* batch, int32_t on);
 int gwb200_poa_batch_get_timers(gwb200_poa_batch* batch, uint64_t* out8);
+/* Windows the device can keep resident at once for this batch's kernel (SMs x CTAs per SM): a batch of at most this many
+ * windows runs as a single wave. */
+int32_t gwb200_poa_batch_resident_windows(gwb200_poa_batch* batch);
 /* sizeof(ScoreT) chosen for this batch (2 or 4), cudapoa_limits.hpp:34-44. */
 int32_t gwb200_poa_batch_score_bytes(const gwb200_poa_batch* batch);
 
