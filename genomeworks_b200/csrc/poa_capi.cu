@@ -564,7 +564,7 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
         b->X.rd_node     = dc.take<uint8_t>(n * static_cast<int64_t>(b->X.rd_capacity) * S);
         b->d_timers      = dc.take<unsigned long long>(n * 8);
         b->X.timers      = nullptr;
-        b->X.pool_bytes  = b->score32 ? 54 * 1024 : 24 * 1024;
+        b->X.pool_bytes  = b->score32 ? 44 * 1024 : 24 * 1024;
         // everything that is left is the score pool (allocate_block.hpp:227-239)
         dc.off                 = align_up64(dc.off, 256);
         P.scores               = b->d_block + dc.off;
@@ -589,7 +589,7 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
         {
             // the v2 kernel stages the read and at least two score rows in its shared-memory pool and packs band starts in 14 bits
             const int64_t max_bw  = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
-            const int64_t pool    = b->score32 ? 54 * 1024 : 24 * 1024;
+            const int64_t pool    = b->score32 ? 44 * 1024 : 24 * 1024;
             const int64_t need    = (b->cfg.max_sequence_size + max_bw + 24) + 2 * (max_bw + 8) * b->score_bytes;
             if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || need > pool)
                 b->use_v2 = false; // first-generation kernel

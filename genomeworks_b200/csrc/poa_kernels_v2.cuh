@@ -580,6 +580,61 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
             loop_count++;
             if (i < t_lo || i > t_hi || j >= J0 + kTileCols || (j > 0 && j - 1 < J0))
                 refill(i, j);
+            // ---- speculative run: lane k assumes the previous k steps were all "diagonal through the first predecessor, which is
+            // the previous row" (the first test of every step, :467-478) and verifies its own step on the tile; the leading
+            // run of successful lanes is exactly what the serial loop would do for those steps, taken at once.
+            {
+                const int32_t ik = i - lane;
+                const int32_t jk = j - lane;
+                bool ok          = ik >= 1 && jk >= 1 && (ik - 1) >= t_lo && (jk - 1) >= J0 && (loop_count - 1 + lane) < limit;
+                int32_t knode    = 0;
+                if (ok)
+                {
+                    const int4 mk = tmeta[ik - t_lo];
+                    knode         = mk.x;
+                    ok            = mk.y == ik - 1; // first predecessor (row 0 for source nodes) is the row above
+                    if (check_band && jk > threshold && jk < max_column - threshold)
+                    {
+                        const int32_t bsk = ((mk.w >> 17) & 0x3fff) << 2;
+                        if (jk <= bsk + threshold || jk >= (bsk + band_width - threshold))
+                            ok = false; // the serial step below performs the abort
+                    }
+                    const int32_t cost = ((mk.w & 0xff) == static_cast<int32_t>(tread[jk - J0])) ? match : mismatch;
+                    const int32_t sij  = tile[(ik - t_lo) * kTileCols + (jk - J0)];
+                    const int32_t sd   = tile[(ik - 1 - t_lo) * kTileCols + (jk - 1 - J0)];
+                    ok                 = ok && (sij == sd + cost);
+                }
+                // the first step uses next_node_id, which must be the node of row i for the speculation to be the serial behaviour
+                const int32_t node0 = __shfl_sync(kFull, knode, 0);
+                uint32_t okmask     = __ballot_sync(kFull, ok);
+                if (node0 != next_node_id)
+                    okmask = 0u;
+                const int32_t run = (okmask == kFull) ? 32 : (__ffs(~okmask) - 1);
+                if (run > 0)
+                {
+                    if (lane < run)
+                    {
+                        aln_graph[aligned_nodes + lane] = static_cast<SizeT>(knode);
+                        aln_read[aligned_nodes + lane]  = static_cast<SizeT>(jk - 1);
+                    }
+                    aligned_nodes += run;
+                    loop_count += run - 1; // the loop header already counted one step
+                    i -= run;
+                    j -= run;
+                    prev_i = i;
+                    prev_j = j;
+                    if (i > 0)
+                    {
+                        const uint32_t r = static_cast<uint32_t>(i - t_lo);
+                        next_node_id     = (r <= static_cast<uint32_t>(t_hi - t_lo)) ? tmeta[r].x : row_meta[i].x;
+                    }
+                    else
+                    {
+                        next_node_id = 0;
+                    }
+                    continue;
+                }
+            }
             const int32_t ti        = i - t_lo;
             const int32_t tj        = j - J0;
             const int32_t scores_ij = tile[ti * kTileCols + tj];
@@ -948,7 +1003,7 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
 }
 
 template <typename ScoreT, typename SizeT, int32_t NW, int32_t MAXC>
-__global__ void __launch_bounds__(32 * NW, 4) poa_window_kernel_v2(const DeviceParams P, const V2Extra X)
+__global__ void __launch_bounds__(32 * NW, (NW == 4 ? 5 : 8)) poa_window_kernel_v2(const DeviceParams P, const V2Extra X)
 {
     const bool MSA = P.msa != 0;
     extern __shared__ __align__(16) uint8_t pool[];
