@@ -972,29 +972,60 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
     __syncwarp();
     if (lane == 0)
     {
-        for (int32_t n = 0; n < p; n++)
+        int32_t n        = 0;
+        int32_t reg_node = -1; // node at position n when the FIFO held nothing else (chain following without the window)
+        while (n < p)
         {
-            const int32_t slot = n & (kQ - 1);
-            const int32_t node = (q_tag[slot] == n) ? q_node[slot] : static_cast<int32_t>(g.sorted[n]);
-            const uint32_t w   = e0w[node];
-            int32_t oc         = 1;
-            if (!(w & 0x8000u))
-                oc = (w == 0x7fffu) ? 0 : static_cast<int32_t>(g.out_cnt[node]);
-            for (int32_t e = 0; e < oc; e++)
+            int32_t node = reg_node;
+            if (node < 0)
             {
-                const int32_t child = (w & 0x8000u) ? static_cast<int32_t>(w & 0x7fffu) : static_cast<int32_t>(g.out_edge(node, e));
+                const int32_t slot = n & (kQ - 1);
+                node               = (q_tag[slot] == n) ? q_node[slot] : static_cast<int32_t>(g.sorted[n]);
+            }
+            reg_node         = -1;
+            const uint32_t w = e0w[node];
+            n++;
+            if (w & 0x8000u)
+            {
+                // exactly one child: the overwhelmingly common case in a POA graph
+                const int32_t child = static_cast<int32_t>(w & 0x7fffu);
                 const uint8_t c     = static_cast<uint8_t>(cnt[child] - 1);
                 cnt[child]          = c;
                 if (c == 0)
                 {
                     g.pos[child] = static_cast<SizeT>(p);
                     g.sorted[p]  = static_cast<SizeT>(child);
-                    if (p - kQ <= n) // slot p % kQ held position p - kQ, already consumed
+                    if (p == n)
+                    {
+                        reg_node = child; // the FIFO was empty: the child is the next node to process
+                    }
+                    else if (p - kQ < n)
                     {
                         q_node[p & (kQ - 1)] = child;
                         q_tag[p & (kQ - 1)]  = p;
                     }
                     p++;
+                }
+            }
+            else if (w != 0x7fffu)
+            {
+                const int32_t oc = g.out_cnt[node];
+                for (int32_t e = 0; e < oc; e++)
+                {
+                    const int32_t child = g.out_edge(node, e);
+                    const uint8_t c     = static_cast<uint8_t>(cnt[child] - 1);
+                    cnt[child]          = c;
+                    if (c == 0)
+                    {
+                        g.pos[child] = static_cast<SizeT>(p);
+                        g.sorted[p]  = static_cast<SizeT>(child);
+                        if (p - kQ < n) // slot p % kQ held position p - kQ, already consumed
+                        {
+                            q_node[p & (kQ - 1)] = child;
+                            q_tag[p & (kQ - 1)]  = p;
+                        }
+                        p++;
+                    }
                 }
             }
         }
