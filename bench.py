@@ -31,6 +31,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 
+# dram bytes (read + write) per window of the dominant kernel, from the committed ncu --set full captures (profiles/)
+NCU_DRAM_BYTES_PER_WINDOW = {"c3": (1.810265e9 + 15.109566e9) / 16, "c2": (4.804323e9 + 9.375816e9) / 1024}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -336,8 +340,12 @@ def main():
                        "l2": "score matrices written per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (cells * sb / 1e9),
                        "windows_ok_last_step": n_ok},
             "dp_cells_per_step_per_gpu": cells, "dp_cells_per_s": cells * world / (k_ms / 1e3),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "poa_window_kernel", "algorithmic_bytes_per_cell": sb,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_DRAM_BYTES_PER_WINDOW.get(args.workload, 0) * n_win or None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per window from the ncu --set full captures in "
+                                           "profiles/r01_poa_v2_{c3,c2}_ncu.md (16 / 1024 windows), scaled to this launch's window count",
+                         "algorithmic_bytes": cells * sb,
+                         "peak_source": peak_src, "kernel": "poa_window_kernel_v2", "algorithmic_bytes_per_cell": sb,
                          "kernel_ms_per_launch": k_ms},
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(timed_launches), "gpu_launches_total": int(launches), "clocks": clocks,

@@ -79,8 +79,8 @@ def run_aligner_bench(args, wp, rank, world, local_rank, barrier, max_over_ranks
                 import ref_lib
                 if ref_lib.have_gwref():
                     al.close()
-                    ref_lib.ref_aligner_run(ql, qd, tl, td, wp["max_bw"])
-                    rr = ref_lib.ref_aligner_run(ql, qd, tl, td, wp["max_bw"])
+                    ref_lib.ref_aligner_run(ql, qd, tl, td, wp["max_bw"], max_device_memory=32 << 30)
+                    rr = ref_lib.ref_aligner_run(ql, qd, tl, td, wp["max_bw"], max_device_memory=32 << 30)
                     same = all((r.convert_to_cigar(True) == rr["cigar_extended"][i]) and (int(r.is_optimal) == rr["is_optimal"][i])
                                for i, r in enumerate(res))
                     line["gpu_reference"] = {"value": n / (rr["timings"][1] / 1e3), "unit": "pairs/s",

@@ -23,6 +23,7 @@ namespace myers
 typedef uint32_t WordType;
 constexpr int32_t kWord       = 32;
 constexpr int32_t kStageCols  = 32;
+constexpr int32_t kStageStride = 33; // words per staged column (+1: lanes that read consecutive columns hit distinct banks)
 constexpr uint32_t kFull      = 0xffffffffu;
 constexpr int32_t kOutOfBand  = INT32_MAX - 1; // myers_gpu.cu:448
 
@@ -374,9 +375,9 @@ struct Stage
         {
             for (int32_t c = 0; c <= jhi - jlo; c++)
             {
-                s_pv[c * 32 + lane] = pvm(lane, jlo + c);
-                s_mv[c * 32 + lane] = mvm(lane, jlo + c);
-                s_sc[c * 32 + lane] = scm(lane, jlo + c);
+                s_pv[c * kStageStride + lane] = pvm(lane, jlo + c);
+                s_mv[c * kStageStride + lane] = mvm(lane, jlo + c);
+                s_sc[c * kStageStride + lane] = scm(lane, jlo + c);
             }
         }
         __syncwarp();
@@ -393,7 +394,7 @@ struct Stage
         WordType p, m;
         if (use_smem)
         {
-            const int32_t o = (j - jlo) * 32 + word_idx;
+            const int32_t o = (j - jlo) * kStageStride + word_idx;
             s = s_sc[o];
             p = s_pv[o];
             m = s_mv[o];
@@ -434,6 +435,22 @@ struct RleWriter
         }
     }
 };
+
+// Appends a run of `run` diagonal steps to the RLE writer; bit k of matchmask = step k is a match (else mismatch).
+__device__ __forceinline__ void rle_append_diagonal_run(RleWriter& W, uint32_t matchmask, int32_t run)
+{
+    int32_t pos = 0;
+    while (pos < run)
+    {
+        const uint32_t bit = (matchmask >> pos) & 1u;
+        const uint32_t x   = (bit ? ~matchmask : matchmask) >> pos; // first position where the state changes
+        int32_t len        = x ? (__ffs(x) - 1) : 32;
+        len                = min(len, run - pos);
+        W.change(bit ? st_match : st_mismatch);
+        W.r_count += len;
+        pos += len;
+    }
+}
 
 // myers_backtrace_banded, myers_gpu.cu:444-627. All lanes walk redundantly (warp-uniform control flow) on staged data;
 // lane 0 writes the RLE path. Returns the number of RLE entries.
@@ -489,6 +506,34 @@ __device__ int32_t backtrace_banded(int32_t lane, Stage& S, int8_t* path, int32_
     {
         if (S.use_smem && j - 1 < S.jlo && j >= 1)
             S.refill(j, lane);
+        if (S.use_smem && i >= 1)
+        {
+            // speculative run of diagonal steps (band row i fixed, j decreasing): lane k evaluates the step at column j - k on the
+            // staged columns; the leading lanes whose step is "neither insertion nor deletion" are exactly the serial steps.
+            const int32_t jk = j - lane;
+            bool ok          = jk >= diagonal_begin && (jk - 1) >= S.jlo;
+            int32_t my = 0, dg = 0;
+            if (ok)
+            {
+                my                  = S.get(i, jk);
+                dg                  = S.get(i, jk - 1);
+                const int32_t above = i <= 1 ? kOutOfBand : S.get(i - 1, jk);
+                const int32_t left  = i >= band_width ? kOutOfBand : S.get(i + 1, jk - 1);
+                ok                  = (left + 1 != my) && (above + 1 != my);
+            }
+            uint32_t okmask = __ballot_sync(kFull, ok);
+            if (__shfl_sync(kFull, my, 0) != myscore)
+                okmask = 0u; // the walk carries an implicit (worst-case) value here, not the matrix entry: take the serial step
+            const int32_t run = (okmask == kFull) ? 32 : (__ffs(~okmask) - 1);
+            if (run > 0)
+            {
+                const uint32_t mm = __ballot_sync(kFull, ok && dg == my);
+                rle_append_diagonal_run(W, mm, run);
+                myscore = __shfl_sync(kFull, dg, run - 1);
+                j -= run;
+                continue;
+            }
+        }
         int32_t r;
         const int32_t above = i <= 1 ? kOutOfBand : S.get(i - 1, j);
         const int32_t diag  = i <= 0 ? j - 1 : S.get(i, j - 1);
@@ -519,6 +564,35 @@ __device__ int32_t backtrace_banded(int32_t lane, Stage& S, int8_t* path, int32_
     {
         if (S.use_smem && j - 1 < S.jlo)
             S.refill(j, lane);
+        if (S.use_smem && i <= band_width)
+        {
+            // speculative run of diagonal steps in the top-left block: lane k evaluates the step at (i - k, j - k)
+            const int32_t ik = i - lane;
+            const int32_t jk = j - lane;
+            bool ok          = ik >= 1 && jk >= 1 && (jk - 1) >= S.jlo;
+            int32_t my = 0, dg = 0;
+            if (ok)
+            {
+                my                  = S.get(ik, jk);
+                const int32_t above = ik == 1 ? jk : S.get(ik - 1, jk);
+                dg                  = ik == 1 ? jk - 1 : S.get(ik - 1, jk - 1);
+                const int32_t left  = S.get(ik, jk - 1);
+                ok                  = (left + 1 != my) && (above + 1 != my);
+            }
+            uint32_t okmask = __ballot_sync(kFull, ok);
+            if (__shfl_sync(kFull, my, 0) != myscore)
+                okmask = 0u; // the walk carries an implicit (worst-case) value here, not the matrix entry: take the serial step
+            const int32_t run = (okmask == kFull) ? 32 : (__ffs(~okmask) - 1);
+            if (run > 0)
+            {
+                const uint32_t mm = __ballot_sync(kFull, ok && dg == my);
+                rle_append_diagonal_run(W, mm, run);
+                myscore = __shfl_sync(kFull, dg, run - 1);
+                i -= run;
+                j -= run;
+                continue;
+            }
+        }
         int32_t r;
         const int32_t above = i == 1 ? j : S.get(i - 1, j);
         const int32_t diag  = i == 1 ? j - 1 : S.get(i - 1, j - 1);
@@ -580,9 +654,9 @@ __device__ __forceinline__ int32_t fetch_task(const DeviceParams& P, int32_t lan
 // myers_banded_kernel, myers_gpu.cu:862-1032
 __global__ void __launch_bounds__(32, 16) myers_banded_kernel(const DeviceParams P)
 {
-    __shared__ WordType s_pv[kStageCols * 32];
-    __shared__ WordType s_mv[kStageCols * 32];
-    __shared__ int32_t s_sc[kStageCols * 32];
+    __shared__ WordType s_pv[kStageCols * kStageStride];
+    __shared__ WordType s_mv[kStageCols * kStageStride];
+    __shared__ int32_t s_sc[kStageCols * kStageStride];
 
     const int32_t lane = threadIdx.x;
     WordType* qpat     = P.qpat + static_cast<int64_t>(blockIdx.x) * P.qpat_elems;

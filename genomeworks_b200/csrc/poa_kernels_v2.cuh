@@ -937,7 +937,8 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
     int32_t* q_node = q_tag + kQ;
     uint8_t* cnt    = pool + kQ * 8;
     uint16_t* e0w   = reinterpret_cast<uint16_t*>(pool + kQ * 8 + nc2);
-    // e0w[n]: 0x8000 | child  -> exactly one out edge;  0x7fff -> no out edge;  0x7ffe -> several (read them from global)
+    // e0w[n]: 0x8000 | child -> exactly one out edge;  0x7fff -> no out edge;  else first child of several (count and the other
+    // children come from global memory, both loads issued together)
     for (int32_t k = lane; k < kQ; k += 32)
         q_tag[k] = -1;
     __syncwarp();
@@ -952,7 +953,7 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
             const int32_t oc = g.out_cnt[n];
             const int32_t e0 = static_cast<uint16_t>(g.out_edge(n, 0));
             cnt[n]           = static_cast<uint8_t>(c);
-            e0w[n]           = static_cast<uint16_t>(oc == 1 ? (0x8000 | e0) : (oc == 0 ? 0x7fff : 0x7ffe));
+            e0w[n]           = static_cast<uint16_t>(oc == 0 ? 0x7fff : (oc == 1 ? (0x8000 | e0) : e0));
         }
         const bool is_src = n < node_count && c == 0;
         const uint32_t m  = __ballot_sync(kFull, is_src);
@@ -1010,11 +1011,16 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
             else if (w != 0x7fffu)
             {
                 const int32_t oc = g.out_cnt[node];
+                int32_t nxt      = g.out_edge(node, 1); // issued together with the count: one memory latency for the common 2-child node
+                int32_t child    = static_cast<int32_t>(w);
                 for (int32_t e = 0; e < oc; e++)
                 {
-                    const int32_t child = g.out_edge(node, e);
-                    const uint8_t c     = static_cast<uint8_t>(cnt[child] - 1);
-                    cnt[child]          = c;
+                    if (e == 1)
+                        child = nxt;
+                    else if (e > 1)
+                        child = g.out_edge(node, e);
+                    const uint8_t c = static_cast<uint8_t>(cnt[child] - 1);
+                    cnt[child]      = c;
                     if (c == 0)
                     {
                         g.pos[child] = static_cast<SizeT>(p);
