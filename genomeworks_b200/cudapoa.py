@@ -183,14 +183,19 @@ class CudaPoaBatch:
         check(lib().gwb200_poa_batch_reset(self._h))
 
     # ---- flat / array interface (bulk callers, tests, bench) -----------------------------------
-    def add_poa_groups_flat(self, win_nseq, seq_len, seq_data):
-        """Bulk add_poa_group: returns (status of the first rejected window or success, number of windows added)."""
+    def add_poa_groups_flat(self, win_nseq, seq_len, seq_data, weights=None):
+        """Bulk add_poa_group: returns (status of the first rejected window or success, number of windows added).
+        weights: optional int8 array with one weight per base, concatenated like seq_data."""
         win_nseq = np.ascontiguousarray(win_nseq, dtype=np.int32)
         seq_len = np.ascontiguousarray(seq_len, dtype=np.int32)
         seq_data = np.ascontiguousarray(seq_data, dtype=np.uint8)
+        wptr = None
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.int8)
+            wptr = weights.ctypes.data
         added = C.c_int32(0)
         rc = check(lib().gwb200_poa_batch_add_groups_flat(self._h, C.c_int32(len(win_nseq)), win_nseq.ctypes.data, seq_len.ctypes.data,
-                                                          seq_data.ctypes.data, None, C.byref(added)))
+                                                          seq_data.ctypes.data, wptr, C.byref(added)))
         return rc, added.value
 
     def get_consensus_arrays(self):

@@ -40,7 +40,7 @@ def _p(a):
 
 def ref_poa_run(win_nseq, seq_len, seq_data, max_seq_size, max_seq_per_poa, band_width, band_mode, adaptive_storage_factor=2.0,
                 graph_length_factor=3.0, max_pred_dist=0, msa=False, gap=-8, mismatch=-6, match=8, mem_fraction=0.5,
-                max_windows_per_batch=0):
+                max_windows_per_batch=0, weights=None):
     """Runs the reference cudapoa; returns dict(consensus, coverage, status, msa, timings)."""
     win_nseq = np.ascontiguousarray(win_nseq, dtype=np.int32)
     seq_len = np.ascontiguousarray(seq_len, dtype=np.int32)
@@ -54,7 +54,9 @@ def ref_poa_run(win_nseq, seq_len, seq_data, max_seq_size, max_seq_per_poa, band
     mc_out = C.c_int32(0)
     timings = np.zeros(3, dtype=np.float64)
     err = C.create_string_buffer(1024)
-    rc = gwref().ref_poa_run(C.c_int32(n), _p(win_nseq), _p(seq_len), _p(seq_data), None, C.c_int32(max_seq_size), C.c_int32(max_seq_per_poa),
+    if weights is not None:
+        weights = np.ascontiguousarray(weights, dtype=np.int8)
+    rc = gwref().ref_poa_run(C.c_int32(n), _p(win_nseq), _p(seq_len), _p(seq_data), _p(weights), C.c_int32(max_seq_size), C.c_int32(max_seq_per_poa),
                              C.c_int32(band_width), C.c_int32(band_mode), C.c_float(adaptive_storage_factor), C.c_float(graph_length_factor),
                              C.c_int32(max_pred_dist), C.c_int32(2 if msa else 1), C.c_int32(gap), C.c_int32(mismatch), C.c_int32(match),
                              C.c_double(mem_fraction), C.c_int32(max_windows_per_batch), _p(cons), _p(cov), _p(status), _p(msa_buf),

@@ -38,10 +38,11 @@ def device_fdiv():
     ol.lib().oracle_set_fdiv(None)
 
 
-def run_ours(win_nseq, seq_len, data, cfg, msa=False, mem=8 << 30):
+def run_ours(win_nseq, seq_len, data, cfg, msa=False, mem=8 << 30, weights=None, gap=-8, mismatch=-6, match=8):
     from genomeworks_b200 import cudapoa
-    batch = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, output_type="msa" if msa else "consensus", config=cfg)
-    rc, added = batch.add_poa_groups_flat(win_nseq, seq_len, data)
+    batch = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, output_type="msa" if msa else "consensus", config=cfg,
+                                 gap_score=gap, mismatch_score=mismatch, match_score=match)
+    rc, added = batch.add_poa_groups_flat(win_nseq, seq_len, data, weights=weights)
     assert rc == 0 and added == len(win_nseq), (rc, added)
     batch.generate_poa()
     if msa:
@@ -187,3 +188,53 @@ def test_batch_api_contracts():
     assert st == [0]
     assert graphs[0].number_of_nodes() == 10 and graphs[0].number_of_edges() == 11
     b.close()
+
+
+def test_weighted_reads_and_other_scores(device_fdiv):
+    """Base weights (Entry::weights) and a non-default scoring scheme, against the oracle and the reference kernels."""
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(20, 350, 9, 10, 5, 5, seed0=4242)
+    rng = np.random.RandomState(3)
+    weights = rng.randint(1, 40, size=int(seq_len.sum()) + 1).astype(np.int8)
+    cfg = cudapoa.make_config(1024, 16, 128, "static_band")
+    for (gap, mismatch, match) in [(-8, -6, 8), (-4, -3, 5)]:
+        ours = run_ours(win_nseq, seq_len, data, cfg, weights=weights, gap=gap, mismatch=mismatch, match=match)
+        windows = synth.split_windows(win_nseq, seq_len, data)
+        wl, off = [], 0
+        for w in windows:
+            ww = []
+            for r in w:
+                ww.append(weights[off:off + len(r)])
+                off += len(r)
+            wl.append(ww)
+        orc = ol.poa_run(windows, _cfg8(cfg), gap=gap, mismatch=mismatch, match=match, weights=wl)
+        assert_same_consensus(ours, orc, "oracle")
+        if ref_lib.have_gwref():
+            ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 128, 1, gap=gap, mismatch=mismatch, match=match, weights=weights)
+            assert_same_consensus(ours, ref, "reference")
+
+
+def test_int32_sizes_long_window_vs_reference():
+    """max_sequence_size 12288 => max_nodes 36864 > INT16_MAX: the <int32 score, int32 size> instantiation (cudapoa_limits.hpp:46-53)."""
+    if not ref_lib.have_gwref():
+        pytest.skip("oracle/_ref/libgwref.so not built")
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(2, 11000, 5, 220, 110, 110, seed0=77, max_read_len=12288)
+    cfg = cudapoa.make_config(12288, 8, 256, "adaptive_band", adaptive_storage_factor=6.0)
+    ours = run_ours(win_nseq, seq_len, data, cfg, mem=24 << 30)
+    ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 12288, 8, 256, 2, adaptive_storage_factor=6.0, mem_fraction=0.3, max_windows_per_batch=2)
+    assert_same_consensus(ours, ref, "reference")
+    assert (ours["status"] == 0).all()
+
+
+def test_static_band_512_and_128_vs_reference():
+    """Other kernel configurations: 1 chunk (band 128, one warp) and 4 chunks (band 512, four warps x one chunk)."""
+    if not ref_lib.have_gwref():
+        pytest.skip("oracle/_ref/libgwref.so not built")
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(40, 900, 10, 20, 12, 12, seed0=555, max_read_len=1024)
+    for bw in (128, 512):
+        cfg = cudapoa.make_config(1024, 16, bw, "static_band")
+        ours = run_ours(win_nseq, seq_len, data, cfg)
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, bw, 1)
+        assert_same_consensus(ours, ref, "reference bw=%d" % bw)
