@@ -356,6 +356,8 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     P.metadata      = a->metadata_d.p;
     P.cells         = a->cells_d.p;
 
+    // residency (kBlocksPerSM) assumes the full shared-memory carve-out regardless of any device-wide cache preference
+    cudaFuncSetAttribute(myers_banded_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     GWB200_CUDA_TRY(cudaEventRecord(a->ev0, a->stream));
     myers_banded_kernel<<<n_blocks, 32, 0, a->stream>>>(P);
     offsets_kernel<<<1, 1024, 0, a->stream>>>(a->path_len_d.p, n, a->offsets_d.p);

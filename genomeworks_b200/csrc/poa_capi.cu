@@ -156,6 +156,17 @@ Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz,
     return s;
 }
 
+// Dynamic shared memory per CTA of the v2 kernel: the staged read (max_sequence_size + widest band) plus a ring of score rows.
+// 44 KB (32-bit scores) / 24 KB (16-bit scores) keep 5 / 8 windows resident per SM and hold >= 4 rows of the widest band for
+// reads up to ~10 kb; longer reads get a larger pool (fewer resident windows, which HBM capacity limits anyway at that size).
+int32_t v2_pool_bytes(const gwb200_poa_batch* b)
+{
+    const int64_t max_bw = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
+    const int64_t dflt   = b->score32 ? 44 * 1024 : 24 * 1024;
+    const int64_t need   = (b->cfg.max_sequence_size + max_bw + 24) + 4 * (max_bw + 8) * b->score_bytes;
+    return static_cast<int32_t>(std::max<int64_t>(dflt, align_up64(need, 1024)));
+}
+
 // Kernel selection for a batch: warps per window and band chunks per warp.
 struct V2Choice
 {
@@ -192,6 +203,9 @@ int32_t v2_action(gwb200_poa_batch* b, int action)
     const int32_t smem = b->X.pool_bytes;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // the kernel's residency is sized against the full shared-memory carve-out; do not inherit a device-wide cache preference
+    // another library set in this process (the reference does cudaDeviceSetCacheConfig(PreferL1), cudapoa_kernels.cuh:605)
+    cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (action == 1)
     {
         int nb = 0;
@@ -564,7 +578,7 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
         b->X.rd_node     = dc.take<uint8_t>(n * static_cast<int64_t>(b->X.rd_capacity) * S);
         b->d_timers      = dc.take<unsigned long long>(n * 8);
         b->X.timers      = nullptr;
-        b->X.pool_bytes  = b->score32 ? 44 * 1024 : 24 * 1024;
+        b->X.pool_bytes  = v2_pool_bytes(b);
         // everything that is left is the score pool (allocate_block.hpp:227-239)
         dc.off                 = align_up64(dc.off, 256);
         P.scores               = b->d_block + dc.off;
@@ -587,11 +601,8 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
         const char* k = std::getenv("GWB200_POA_KERNEL"); // development A/B switch: "v1" selects the first-generation kernel
         b->use_v2     = !(k && std::string(k) == "v1");
         {
-            // the v2 kernel stages the read and at least two score rows in its shared-memory pool and packs band starts in 14 bits
-            const int64_t max_bw  = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
-            const int64_t pool    = b->score32 ? 44 * 1024 : 24 * 1024;
-            const int64_t need    = (b->cfg.max_sequence_size + max_bw + 24) + 2 * (max_bw + 8) * b->score_bytes;
-            if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || need > pool)
+            // the v2 kernel packs band starts in 15 bits (x4) and needs its staged read plus a few score rows in shared memory
+            if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || b->X.pool_bytes > 200 * 1024)
                 b->use_v2 = false; // first-generation kernel
         }
         const char* nwv = std::getenv("GWB200_POA_WARPS"); // development switch: warps per window (1, 2 or 4)
