@@ -156,17 +156,6 @@ Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz,
     return s;
 }
 
-// Dynamic shared memory per CTA of the v2 kernel: the staged read (max_sequence_size + widest band) plus a ring of score rows.
-// 44 KB (32-bit scores) / 24 KB (16-bit scores) keep 5 / 8 windows resident per SM and hold >= 4 rows of the widest band for
-// reads up to ~10 kb; longer reads get a larger pool (fewer resident windows, which HBM capacity limits anyway at that size).
-int32_t v2_pool_bytes(const gwb200_poa_batch* b)
-{
-    const int64_t max_bw = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
-    const int64_t dflt   = b->score32 ? 44 * 1024 : 24 * 1024;
-    const int64_t need   = (b->cfg.max_sequence_size + max_bw + 24) + 4 * (max_bw + 8) * b->score_bytes;
-    return static_cast<int32_t>(std::max<int64_t>(dflt, align_up64(need, 1024)));
-}
-
 // Kernel selection for a batch: warps per window and band chunks per warp.
 struct V2Choice
 {
@@ -193,6 +182,19 @@ V2Choice choose_v2(const gwb200_poa_batch* b)
     if (nw == 2)
         return {2, 1};
     return {1, 1};
+}
+
+// Dynamic shared memory per CTA of the v2 kernel: the staged read (max_sequence_size + widest band) plus a ring of score rows.
+// 44 KB (32-bit scores) / 24 KB (16-bit scores) keep 5 / 8 windows resident per SM and hold >= 4 rows of the widest band for
+// reads up to ~10 kb; longer reads get a larger pool (fewer resident windows, which HBM capacity limits anyway at that size).
+int32_t v2_pool_bytes(const gwb200_poa_batch* b)
+{
+    const int64_t max_bw = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
+    int64_t dflt         = b->score32 ? 44 * 1024 : 24 * 1024;
+    if (!b->score32 && choose_v2(b).nw == 1)
+        dflt = 12 * 1024; // one-warp kernels (127 registers, __launch_bounds__(32, 16)): 16 windows per SM
+    const int64_t need   = (b->cfg.max_sequence_size + max_bw + 24) + 4 * (max_bw + 8) * b->score_bytes;
+    return static_cast<int32_t>(std::max<int64_t>(dflt, align_up64(need, 1024)));
 }
 
 // action 0: launch; action 1: return resident CTAs per SM (occupancy) for the chosen kernel
