@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgwb200.so")
+LIB_PATH = os.environ.get("GWB200_LIB_PATH") or os.path.join(_HERE, "libgwb200.so")  # env override: profiling builds only
 _lib = None
 
 E_INVALID_ARGUMENT = -1

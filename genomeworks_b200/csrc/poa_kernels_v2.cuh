@@ -124,6 +124,15 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
     Band<ScoreT> B{scores, band_width, band_shift, max_column, band_width + kRightPad, gradient};
     const int32_t stride = B.stride;
     const int32_t nchunks = band_width / 128;
+    // warps that take part in the DP rows of this alignment: one per chunk, at most NW; warps without a chunk skip the rows
+    // (and their per-row preamble) and wait at the barrier after them
+    const int32_t nw_eff = min(NW, nchunks);
+    auto row_sync = [&]() {
+        if (NW == 1 || nw_eff == 1)
+            __syncwarp();
+        else
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * nw_eff) : "memory");
+    };
 
     // ---- shared memory during the DP phase: [ staged read | ring of the most recent score rows (row r in slot r % R) ]
     const int32_t sread_bytes = (read_length + band_width + 8 + 15) & ~15;
@@ -176,10 +185,13 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
             nx_bsp0            = B.start(nx_p0);
         }
     }
+#ifdef GWB200_ROW_PROFILE
+    unsigned long long rp_a = 0, rp_b = 0;
+#endif
     int32_t ring_slot = 0; // slot of the current row = row % R, maintained incrementally
     const int32_t G   = 128 * gap;
 
-    for (int32_t r0 = 1; r0 <= graph_count; r0 += 32)
+    for (int32_t r0 = 1; r0 <= graph_count && warp < nw_eff; r0 += 32)
     {
         const int32_t cur_node = nx_node, cur_misc = nx_misc, cur_p0 = nx_p0, cur_p1 = nx_p1, cur_bs = nx_bs, cur_bsp0 = nx_bsp0;
         const int32_t nrows    = min(32, graph_count - r0 + 1);
@@ -223,6 +235,9 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                     }
                 }
             }
+#ifdef GWB200_ROW_PROFILE
+            const unsigned long long rp_t0 = clock64();
+#endif
             const int32_t row  = r0 + k;
             const int32_t misc = __shfl_sync(kFull, cur_misc, k);
             const int32_t p0   = __shfl_sync(kFull, cur_p0, k);
@@ -284,7 +299,7 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
 #pragma unroll
                 for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
                 {
-                    const int32_t c = warp + ci * NW;
+                    const int32_t c = warp + ci * nw_eff;
                     if (c < nchunks)
                     {
                         const int32_t read_pos = bs + c * 128 + 4 * lane;
@@ -360,7 +375,7 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                 carry0 = (pc == 0) ? 0 : first;
                 for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
                 {
-                    const int32_t c = warp + ci * NW;
+                    const int32_t c = warp + ci * nw_eff;
                     if (c < nchunks)
                     {
                         const int32_t read_pos = bs + c * 128 + 4 * lane;
@@ -409,10 +424,13 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                     }
                 }
             }
-            if (NW > 1)
-                __syncthreads();
-            else
-                __syncwarp();
+#ifdef GWB200_ROW_PROFILE
+            const unsigned long long rp_t1 = clock64();
+#endif
+            row_sync();
+#ifdef GWB200_ROW_PROFILE
+            const unsigned long long rp_t2 = clock64();
+#endif
 
             // ---- phase 2: carry into every chunk by a lane-wise max-plus scan over the chunk-out values, final values, stores
             int32_t cin_lane;
@@ -433,7 +451,7 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
 #pragma unroll
             for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
             {
-                const int32_t c = warp + ci * NW;
+                const int32_t c = warp + ci * nw_eff;
                 if (c < nchunks)
                 {
                     const int32_t cin   = __shfl_sync(kFull, cin_lane, c);
@@ -473,12 +491,32 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                     }
                 }
             }
-            if (NW > 1)
-                __syncthreads();
+#ifdef GWB200_ROW_PROFILE
+            const unsigned long long rp_t3 = clock64();
+#endif
+            row_sync();
+#ifdef GWB200_ROW_PROFILE
+            const unsigned long long rp_t4 = clock64();
+            if (GWB200_ROW_PROFILE == 1)
+            {
+                rp_a += rp_t1 - rp_t0;
+                rp_b += rp_t2 - rp_t1;
+            }
             else
-                __syncwarp();
+            {
+                rp_a += rp_t3 - rp_t2;
+                rp_b += rp_t4 - rp_t3;
+            }
+#endif
         }
     }
+#ifdef GWB200_ROW_PROFILE
+    if (timers && threadIdx.x == 0)
+    {
+        timers[6] += rp_a;
+        timers[7] += rp_b;
+    }
+#endif
     GWB200_TIMER_LAP(0);
 
     int32_t result = 0;
@@ -520,6 +558,7 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
     ScoreT* tile = reinterpret_cast<ScoreT*>(pool);                                         // [kTileRows][kTileCols]
     int4* tmeta  = reinterpret_cast<int4*>(pool + kTileRows * kTileCols * sizeof(ScoreT)); // [kTileRows]
     uint8_t* tread = reinterpret_cast<uint8_t*>(tmeta + kTileRows);                          // read[J0 - 1 + k], k in [0, 66)
+    int8_t* tjump  = reinterpret_cast<int8_t*>(tread + 72);                                  // [5][kTileRows]: 2^m-th pred0 ancestor
     int32_t t_lo = 1, t_hi = 0, J0 = 0; // tile rows [t_lo, t_hi], columns [J0, J0 + kTileCols)
 
     auto refill = [&](int32_t ri, int32_t rj) {
@@ -529,8 +568,24 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
         J0   = max(0, rj - (kTileCols - 2)) & ~1;
         {
             const int32_t row = t_lo + lane; // metadata: lane k <-> row t_lo + k
+            int32_t up        = -1;          // tile-relative row of the first predecessor, -1 = none inside the tile
             if (row <= t_hi)
-                tmeta[lane] = row >= 1 ? row_meta[row] : make_int4(0, 0, 0, 0);
+            {
+                const int4 mm = row >= 1 ? row_meta[row] : make_int4(0, 0, 0, 0);
+                tmeta[lane]   = mm;
+                if (row >= 1 && mm.y >= t_lo)
+                    up = mm.y - t_lo;
+            }
+            // pointer doubling over the first-predecessor links: tjump[m][r] = 2^m-th ancestor of tile row r (or -1)
+            tjump[lane] = static_cast<int8_t>(up);
+#pragma unroll
+            for (int32_t m = 1; m < 5; m++)
+            {
+                __syncwarp();
+                if (up >= 0)
+                    up = tjump[(m - 1) * kTileRows + up];
+                tjump[m * kTileRows + lane] = static_cast<int8_t>(up);
+            }
         }
         for (int32_t k = lane; k < kTileCols + 2; k += 32)
         {
@@ -580,29 +635,41 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
             loop_count++;
             if (i < t_lo || i > t_hi || j >= J0 + kTileCols || (j > 0 && j - 1 < J0))
                 refill(i, j);
-            // ---- speculative run: lane k assumes the previous k steps were all "diagonal through the first predecessor, which is
-            // the previous row" (the first test of every step, :467-478) and verifies its own step on the tile; the leading
-            // run of successful lanes is exactly what the serial loop would do for those steps, taken at once.
+            // ---- speculative run: lane k assumes the previous k steps were all "diagonal through the first predecessor" (the
+            // first test of every step, :467-478), finds the row it would stand on by following k first-predecessor links
+            // (binary decomposition of k over the tile's pointer-doubling tables) and verifies its own step on the tile; the
+            // leading run of successful lanes is exactly what the serial loop would do for those steps, taken at once.
             {
-                const int32_t ik = i - lane;
+                int32_t pos = i - t_lo; // tile-relative row after `lane` steps, -1 = outside the tile
+#pragma unroll
+                for (int32_t m = 0; m < 5; m++)
+                {
+                    if (((lane >> m) & 1) && pos >= 0)
+                        pos = tjump[m * kTileRows + pos];
+                }
+                const int32_t ik = t_lo + pos;
                 const int32_t jk = j - lane;
-                bool ok          = ik >= 1 && jk >= 1 && (ik - 1) >= t_lo && (jk - 1) >= J0 && (loop_count - 1 + lane) < limit;
-                int32_t knode    = 0;
+                bool ok          = pos >= 0 && ik >= 1 && jk >= 1 && (jk - 1) >= J0 && (loop_count - 1 + lane) < limit;
+                int32_t knode = 0, kup = 0;
                 if (ok)
                 {
-                    const int4 mk = tmeta[ik - t_lo];
+                    const int4 mk = tmeta[pos];
                     knode         = mk.x;
-                    ok            = mk.y == ik - 1; // first predecessor (row 0 for source nodes) is the row above
+                    kup           = mk.y; // first predecessor row (row 0 for source nodes)
+                    ok            = kup >= t_lo;
                     if (check_band && jk > threshold && jk < max_column - threshold)
                     {
                         const int32_t bsk = ((mk.w >> 17) & 0x3fff) << 2;
                         if (jk <= bsk + threshold || jk >= (bsk + band_width - threshold))
                             ok = false; // the serial step below performs the abort
                     }
-                    const int32_t cost = ((mk.w & 0xff) == static_cast<int32_t>(tread[jk - J0])) ? match : mismatch;
-                    const int32_t sij  = tile[(ik - t_lo) * kTileCols + (jk - J0)];
-                    const int32_t sd   = tile[(ik - 1 - t_lo) * kTileCols + (jk - 1 - J0)];
-                    ok                 = ok && (sij == sd + cost);
+                    if (ok)
+                    {
+                        const int32_t cost = ((mk.w & 0xff) == static_cast<int32_t>(tread[jk - J0])) ? match : mismatch;
+                        const int32_t sij  = tile[pos * kTileCols + (jk - J0)];
+                        const int32_t sd   = tile[(kup - t_lo) * kTileCols + (jk - 1 - J0)];
+                        ok                 = sij == sd + cost;
+                    }
                 }
                 // the first step uses next_node_id, which must be the node of row i for the speculation to be the serial behaviour
                 const int32_t node0 = __shfl_sync(kFull, knode, 0);
@@ -619,7 +686,7 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                     }
                     aligned_nodes += run;
                     loop_count += run - 1; // the loop header already counted one step
-                    i -= run;
+                    i = __shfl_sync(kFull, kup, run - 1);
                     j -= run;
                     prev_i = i;
                     prev_j = j;

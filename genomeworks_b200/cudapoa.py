@@ -244,7 +244,11 @@ class CudaPoaBatch:
         """Per-phase cycle counters summed over windows: DP rows, end cell, traceback, add-alignment, topsort, consensus/MSA."""
         out = np.zeros(8, dtype=np.uint64)
         check(lib().gwb200_poa_batch_get_timers(self._h, out.ctypes.data))
-        return dict(zip(["dp_rows", "end_cell", "traceback", "add_alignment", "topsort", "consensus"], [int(x) for x in out[:6]]))
+        names = ["dp_rows", "end_cell", "traceback", "add_alignment", "topsort", "consensus"]
+        d = dict(zip(names, [int(x) for x in out[:6]]))
+        if out[6] or out[7]:  # row-level probes of a -DGWB200_ROW_PROFILE build
+            d["aux6"], d["aux7"] = int(out[6]), int(out[7])
+        return d
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

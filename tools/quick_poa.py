@@ -38,7 +38,10 @@ for it in range(3):
     print("ours: generate+get %.1f ms, kernel %.2f ms, cells %.3e, ok=%d  -> %.0f windows/s" % ((t2 - t1) * 1e3, b.last_kernel_ms(), b.last_cells(),
                                                                                              int((st == 0).sum()), n / (b.last_kernel_ms() / 1e3)), flush=True)
 tm = b.get_timers()
+aux = {k: tm.pop(k) for k in ("aux6", "aux7") if k in tm}
 tot = max(1, sum(tm.values()))
+if aux:
+    print("row probes (share of dp_rows):", {k: "%.1f%%" % (100.0 * v / max(1, tm["dp_rows"])) for k, v in aux.items()})
 print("phase shares:", {k: "%.1f%%" % (100.0 * v / tot) for k, v in tm.items()}, "cycles/window %.3e" % (tot / n), flush=True)
 ours = [bytes(c[i, :lens[i]]).decode() for i in range(n)]
 b.close()
