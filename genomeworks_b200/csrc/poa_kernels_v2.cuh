@@ -15,6 +15,7 @@
 //   topsort      same Kahn FIFO order (cudapoa_topsort.cuh:45-97), in-degree counters and the queue window in shared
 //                memory, children's adjacency fetched when they are enqueued.
 #pragma once
+#include <type_traits>
 
 #include "poa_kernels.cuh"
 
@@ -984,27 +985,19 @@ __device__ int32_t add_alignment_v2(const Win<SizeT>& g, int32_t& node_count_io,
     return error;
 }
 
-// topologicalSortDeviceUtil (cudapoa_topsort.cuh:45-97): same Kahn FIFO order. When the graph fits the shared-memory pool
-// (16-bit node ids), the in-degree counters, a compressed "only child" word per node and a window of the FIFO are staged
-// in shared memory by coalesced loads, and the serial walk touches global memory only to write sorted[] / pos[].
-template <typename SizeT>
-__device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* pool, int32_t pool_bytes)
+// topologicalSortDeviceUtil (cudapoa_topsort.cuh:45-97): same Kahn FIFO order. The in-degree counters (u8) and a 64-entry
+// tagged window of the FIFO live in the shared-memory pool; a compressed "only child" word per node (SizeT wide) lives in the
+// pool too when it fits and in a global scratch array otherwise (chains run along consecutive node ids, so those loads hit L1).
+// Both are filled by coalesced loads; the serial walk touches the adjacency arrays only at branching nodes and global memory
+// otherwise only to write sorted[] / pos[].
+template <typename SizeT, typename WordT>
+__device__ void topsort_walk(const Win<SizeT>& g, int32_t node_count, int32_t* q_tag, int32_t* q_node, uint8_t* cnt, WordT* e0w)
 {
-    const int32_t lane = threadIdx.x & 31;
-    constexpr int32_t kQ = 64;
-    const int32_t nc2    = (node_count + 1) & ~1;
-    if (sizeof(SizeT) != 2 || kQ * 8 + nc2 + 2 * node_count + 16 > pool_bytes)
-    {
-        if (lane == 0)
-            topsort(g, node_count);
-        __syncwarp();
-        return;
-    }
-    int32_t* q_tag  = reinterpret_cast<int32_t*>(pool);
-    int32_t* q_node = q_tag + kQ;
-    uint8_t* cnt    = pool + kQ * 8;
-    uint16_t* e0w   = reinterpret_cast<uint16_t*>(pool + kQ * 8 + nc2);
-    // e0w[n]: 0x8000 | child -> exactly one out edge;  0x7fff -> no out edge;  else first child of several (count and the other
+    const int32_t lane     = threadIdx.x & 31;
+    constexpr int32_t kQ   = 64;
+    constexpr WordT kOne   = static_cast<WordT>(1) << (8 * sizeof(WordT) - 1); // flag: exactly one out edge
+    constexpr WordT kNone  = static_cast<WordT>(kOne - 1);                     // no out edge
+    // e0w[n]: kOne | child -> exactly one out edge;  kNone -> no out edge;  else first child of several (count and the other
     // children come from global memory, both loads issued together)
     for (int32_t k = lane; k < kQ; k += 32)
         q_tag[k] = -1;
@@ -1018,9 +1011,9 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
         {
             c                = g.in_cnt[n];
             const int32_t oc = g.out_cnt[n];
-            const int32_t e0 = static_cast<uint16_t>(g.out_edge(n, 0));
+            const WordT e0   = static_cast<WordT>(static_cast<WordT>(g.out_edge(n, 0)) & kNone);
             cnt[n]           = static_cast<uint8_t>(c);
-            e0w[n]           = static_cast<uint16_t>(oc == 0 ? 0x7fff : (oc == 1 ? (0x8000 | e0) : e0));
+            e0w[n]           = static_cast<WordT>(oc == 0 ? kNone : (oc == 1 ? (kOne | e0) : e0));
         }
         const bool is_src = n < node_count && c == 0;
         const uint32_t m  = __ballot_sync(kFull, is_src);
@@ -1050,13 +1043,13 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
                 const int32_t slot = n & (kQ - 1);
                 node               = (q_tag[slot] == n) ? q_node[slot] : static_cast<int32_t>(g.sorted[n]);
             }
-            reg_node         = -1;
-            const uint32_t w = e0w[node];
+            reg_node      = -1;
+            const WordT w = e0w[node];
             n++;
-            if (w & 0x8000u)
+            if (w & kOne)
             {
                 // exactly one child: the overwhelmingly common case in a POA graph
-                const int32_t child = static_cast<int32_t>(w & 0x7fffu);
+                const int32_t child = static_cast<int32_t>(w & kNone);
                 const uint8_t c     = static_cast<uint8_t>(cnt[child] - 1);
                 cnt[child]          = c;
                 if (c == 0)
@@ -1075,7 +1068,7 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
                     p++;
                 }
             }
-            else if (w != 0x7fffu)
+            else if (w != kNone)
             {
                 const int32_t oc = g.out_cnt[node];
                 int32_t nxt      = g.out_edge(node, 1); // issued together with the count: one memory latency for the common 2-child node
@@ -1104,6 +1097,33 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
         }
     }
     __syncwarp();
+}
+
+// `scratch`: a per-window global array of at least max_nodes SizeT-sized words that is free during the sort (cons_preds)
+template <typename SizeT>
+__device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* pool, int32_t pool_bytes, void* scratch)
+{
+    using WordT          = typename std::conditional<sizeof(SizeT) == 2, uint16_t, uint32_t>::type;
+    constexpr int32_t kQ = 64;
+    const int32_t nc4    = (node_count + 3) & ~3;
+    const int32_t fixed  = kQ * 8 + nc4 + 16;
+    int32_t* q_tag       = reinterpret_cast<int32_t*>(pool);
+    int32_t* q_node      = q_tag + kQ;
+    uint8_t* cnt         = pool + kQ * 8;
+    if (fixed + static_cast<int32_t>(sizeof(WordT)) * node_count <= pool_bytes)
+    {
+        topsort_walk<SizeT, WordT>(g, node_count, q_tag, q_node, cnt, reinterpret_cast<WordT*>(pool + kQ * 8 + nc4));
+    }
+    else if (fixed <= pool_bytes)
+    {
+        topsort_walk<SizeT, WordT>(g, node_count, q_tag, q_node, cnt, static_cast<WordT*>(scratch));
+    }
+    else
+    {
+        if ((threadIdx.x & 31) == 0)
+            topsort(g, node_count);
+        __syncwarp();
+    }
 }
 
 template <typename ScoreT, typename SizeT, int32_t NW, int32_t MAXC>
@@ -1250,7 +1270,7 @@ __global__ void __launch_bounds__(32 * NW, (NW == 4 ? 5 : (NW == 1 ? 16 : 8))) p
                 int32_t e  = add_alignment_v2<SizeT>(g, nc, alen, aln_graph, sequence, seq_len, aln_read, base_weights, path, rd_node);
                 GWB200_TIMER_LAP(3);
                 if (!e)
-                    topsort_v2<SizeT>(g, nc, pool, X.pool_bytes);
+                    topsort_v2<SizeT>(g, nc, pool, X.pool_bytes, static_cast<SizeT*>(P.cons_preds) + w * mn);
                 GWB200_TIMER_LAP(4);
                 if (lane == 0)
                 {
