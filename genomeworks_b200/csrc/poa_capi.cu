@@ -173,6 +173,8 @@ V2Choice choose_v2(const gwb200_poa_batch* b)
         nw = 1;
     if (b->nw_override > 0 && !adaptive && nchunks <= 4)
         nw = b->nw_override; // development switch
+    if (b->nw_override > 0 && adaptive)
+        return b->nw_override == 1 ? V2Choice{1, 12} : (b->nw_override == 2 ? V2Choice{2, 6} : V2Choice{4, 3}); // development switch
     if (nw == 1 && nchunks == 2)
         return {1, 2};
     if (nchunks > 4 || nw < std::min(nchunks, 4))
@@ -184,16 +186,20 @@ V2Choice choose_v2(const gwb200_poa_batch* b)
     return {1, 1};
 }
 
-// Dynamic shared memory per CTA of the v2 kernel: the staged read (max_sequence_size + widest band) plus a ring of score rows.
-// 44 KB (32-bit scores) / 24 KB (16-bit scores) keep 5 / 8 windows resident per SM and hold >= 4 rows of the widest band for
-// reads up to ~10 kb; longer reads get a larger pool (fewer resident windows, which HBM capacity limits anyway at that size).
+// Dynamic shared memory per CTA of the v2 kernel: the staged read (max_sequence_size + widest band) plus a ring of score rows;
+// the traceback tile and the topological-sort staging reuse it. Defaults: 31 KB (32-bit scores; 7 windows per SM for the
+// 4-warp kernels, measured best of 5..8 on C3), 24 KB (16-bit scores), 12 KB (one-warp kernels with 16-bit scores, 16 per SM).
+// Reads longer than ~10 kb get a pool that holds the staged read plus two rows of the widest band (fewer resident windows,
+// which HBM capacity limits anyway at that size).
 int32_t v2_pool_bytes(const gwb200_poa_batch* b)
 {
     const int64_t max_bw = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
-    int64_t dflt         = b->score32 ? 44 * 1024 : 24 * 1024;
-    if (!b->score32 && choose_v2(b).nw == 1)
-        dflt = 12 * 1024; // one-warp kernels (127 registers, __launch_bounds__(32, 16)): 16 windows per SM
-    const int64_t need   = (b->cfg.max_sequence_size + max_bw + 24) + 4 * (max_bw + 8) * b->score_bytes;
+    int64_t dflt         = b->score32 ? 31 * 1024 : 24 * 1024;
+    if (choose_v2(b).nw == 1)
+        dflt = b->score32 ? 24 * 1024 : 12 * 1024; // one-warp kernels (127 registers, __launch_bounds__(32, 16)): up to 16 windows per SM
+    const int64_t need   = (b->cfg.max_sequence_size + max_bw + 24) + 2 * (max_bw + 8) * b->score_bytes;
+    if (const char* kb = std::getenv("GWB200_POA_POOL_KB")) // development switch
+        return std::atoi(kb) * 1024;
     return static_cast<int32_t>(std::max<int64_t>(dflt, align_up64(need, 1024)));
 }
 
@@ -237,6 +243,10 @@ int32_t typed_action(gwb200_poa_batch* b, int action)
         int32_t r;
         if (ch.nw == 1 && ch.maxc == 2)
             r = v2_action<ScoreT, SizeT, 1, 2>(b, action);
+        else if (ch.nw == 1 && ch.maxc == 12)
+            r = v2_action<ScoreT, SizeT, 1, 12>(b, action);
+        else if (ch.nw == 2 && ch.maxc == 6)
+            r = v2_action<ScoreT, SizeT, 2, 6>(b, action);
         else if (ch.nw == 4 && ch.maxc == 3)
             r = v2_action<ScoreT, SizeT, 4, 3>(b, action);
         else if (ch.nw == 4)
@@ -471,6 +481,10 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     b->size_bytes       = b->size32 ? 4 : 2;
     b->msa              = (output_mask & GWB200_POA_OUTPUT_MSA) != 0;
     b->bid              = gwb200_poa_batch::batches++;
+    {
+        const char* nwv = std::getenv("GWB200_POA_WARPS"); // development switch: warps per window (1, 2 or 4)
+        b->nw_override  = nwv ? std::atoi(nwv) : 0;
+    }
 
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
@@ -607,8 +621,6 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
             if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || b->X.pool_bytes > 200 * 1024)
                 b->use_v2 = false; // first-generation kernel
         }
-        const char* nwv = std::getenv("GWB200_POA_WARPS"); // development switch: warps per window (1, 2 or 4)
-        b->nw_override  = nwv ? std::atoi(nwv) : 0;
     }
     gwb200_poa_batch_reset(b);
     *out = b;

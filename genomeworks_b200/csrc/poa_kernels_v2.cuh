@@ -24,6 +24,9 @@ namespace gwb200
 namespace poa
 {
 
+#ifndef GWB200_POA_NW4_BLOCKS
+#define GWB200_POA_NW4_BLOCKS 7 // resident windows per SM the 4-warp kernels are compiled for (72 registers; measured best of 5..8)
+#endif
 constexpr int32_t kTileRows = 32;
 constexpr int32_t kTileCols = 64;
 
@@ -1127,7 +1130,7 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
 }
 
 template <typename ScoreT, typename SizeT, int32_t NW, int32_t MAXC>
-__global__ void __launch_bounds__(32 * NW, (NW == 4 ? 5 : (NW == 1 ? 16 : 8))) poa_window_kernel_v2(const DeviceParams P, const V2Extra X)
+__global__ void __launch_bounds__(32 * NW, (NW == 4 ? GWB200_POA_NW4_BLOCKS : (NW == 1 ? 16 : 10))) poa_window_kernel_v2(const DeviceParams P, const V2Extra X)
 {
     const bool MSA = P.msa != 0;
     extern __shared__ __align__(16) uint8_t pool[];

@@ -1,5 +1,5 @@
 """Development aid: time a POA config (ours, optional v1 A/B via GWB200_POA_KERNEL=v1) and print per-phase cycle shares.
-usage: quick_poa.py {c2|c3} [n_windows] [--ref]"""
+usage: quick_poa.py {c2|c3} [n_windows] [--ref] [--factor F]   (env GWB200_POA_WARPS / GWB200_POA_POOL_KB: kernel experiments)"""
 import os
 import sys
 import time
@@ -20,13 +20,15 @@ if which == "c2":
     ref_args = (1024, 16, 256, 1)
     factor = 2.0
 else:
-    win_nseq, seq_len, data = synth.poa_windows(n, 10000, 32, 200, 100, 100, seed0=1000, max_read_len=10240)
-    cfg = cudapoa.make_config(10240, 32, 256, "adaptive_band", adaptive_storage_factor=6.0)
-    mem = int(n * 215e6) + (2 << 30)
-    ref_args = (10240, 32, 256, 2)
-    factor = 6.0
+    factor = float(sys.argv[sys.argv.index("--factor") + 1]) if "--factor" in sys.argv else 6.0
+    L = int(sys.argv[sys.argv.index("--len") + 1]) if "--len" in sys.argv else 10000  # window length (C3: 10 kb)
+    mseq = (L + 1023) // 1024 * 1024
+    win_nseq, seq_len, data = synth.poa_windows(n, L, 32, L // 50, L // 100, L // 100, seed0=1000, max_read_len=mseq)
+    cfg = cudapoa.make_config(mseq, 32, 256, "adaptive_band", adaptive_storage_factor=factor)
+    mem = int(n * (factor * 32.5e6 + 20e6) * mseq / 10240) + (2 << 30)
+    ref_args = (mseq, 32, 256, 2)
 b = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, config=cfg)
-print("kernel", os.environ.get("GWB200_POA_KERNEL", "v2"), "max_poas", b.max_poas, flush=True)
+print("kernel", os.environ.get("GWB200_POA_KERNEL", "v2"), "max_poas", b.max_poas, "resident", b.resident_windows, flush=True)
 for it in range(3):
     b.reset()
     b.add_poa_groups_flat(win_nseq, seq_len, data)
