@@ -174,34 +174,44 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
 
     // ---- per-row metadata: fetched 32 rows at a time by the lanes, one group ahead of its use (every warp keeps its own
     // copy, the loads hit L1); warp 0 also writes it to row_meta for the end-cell search and the traceback.
-    int32_t nx_node = 0, nx_misc = 0, nx_p0 = 0, nx_p1 = 0, nx_bs = 0, nx_bsp0 = 0;
+    // packed per-row words (broadcast by three shuffles per row):
+    //   misc: base | in-degree << 8 | sink << 16 | (band start / 4) << 17        (also what row_meta.w holds)
+    //   w1  : band start of predecessor 0 | band start of predecessor 1 << 16
+    //   w2  : min(row - pred0 row, 255) | min(row - pred1 row, 255) << 8 | "both predecessors are in the ring" << 16
+    int32_t nx_node = 0, nx_misc = 0, nx_p0 = 0, nx_p1 = 0, nx_w1 = 0, nx_w2 = 0;
+    auto pack_row = [&](int32_t row, int32_t node, int32_t base, int32_t pc, int32_t oc, int32_t e0, int32_t e1) {
+        nx_node           = node;
+        nx_p0             = pc > 0 ? static_cast<int32_t>(g.pos[e0]) + 1 : 0;
+        nx_p1             = pc > 1 ? static_cast<int32_t>(g.pos[e1]) + 1 : 0;
+        nx_misc           = base | (pc << 8) | ((oc == 0 ? 1 : 0) << 16) | ((B.start(row) >> 2) << 17);
+        nx_w1             = B.start(nx_p0) | (B.start(nx_p1) << 16);
+        const int32_t d0  = min(row - nx_p0, 255);
+        const int32_t d1  = min(row - nx_p1, 255);
+        const bool inring = use_ring && pc <= 2 && d0 < R && (pc < 2 || d1 < R);
+        nx_w2             = d0 | (d1 << 8) | ((inring ? 1 : 0) << 16);
+    };
     {
         const int32_t row = 1 + lane;
         if (row <= graph_count)
         {
             const int32_t node = g.sorted[row - 1];
-            const int32_t pc   = g.in_cnt[node];
-            nx_node            = node;
-            nx_misc            = static_cast<int32_t>(g.nodes[node]) | (pc << 8) | ((g.out_cnt[node] == 0 ? 1 : 0) << 16);
-            nx_p0              = pc > 0 ? static_cast<int32_t>(g.pos[g.in_edge(node, 0)]) + 1 : 0;
-            nx_p1              = pc > 1 ? static_cast<int32_t>(g.pos[g.in_edge(node, 1)]) + 1 : 0;
-            nx_bs              = B.start(row);
-            nx_bsp0            = B.start(nx_p0);
+            pack_row(row, node, g.nodes[node], g.in_cnt[node], g.out_cnt[node], g.in_edge(node, 0), g.in_edge(node, 1));
         }
     }
 #ifdef GWB200_ROW_PROFILE
     unsigned long long rp_a = 0, rp_b = 0;
 #endif
     int32_t ring_slot = 0; // slot of the current row = row % R, maintained incrementally
+    ScoreT* rowp      = scores; // row pointer in global memory, bumped once per row
     const int32_t G   = 128 * gap;
 
     for (int32_t r0 = 1; r0 <= graph_count && warp < nw_eff; r0 += 32)
     {
-        const int32_t cur_node = nx_node, cur_misc = nx_misc, cur_p0 = nx_p0, cur_p1 = nx_p1, cur_bs = nx_bs, cur_bsp0 = nx_bsp0;
+        const int32_t cur_node = nx_node, cur_misc = nx_misc, cur_p0 = nx_p0, cur_p1 = nx_p1, cur_w1 = nx_w1, cur_w2 = nx_w2;
         const int32_t nrows    = min(32, graph_count - r0 + 1);
         const bool have_next   = r0 + 32 <= graph_count;
         if (warp == 0 && lane < nrows)
-            row_meta[r0 + lane] = make_int4(cur_node, cur_p0, cur_p1, cur_misc | ((cur_bs >> 2) << 17));
+            row_meta[r0 + lane] = make_int4(cur_node, cur_p0, cur_p1, cur_misc);
         const int32_t nrow = r0 + 32 + lane;
         const bool nvalid  = have_next && nrow <= graph_count;
         int32_t t_node = 0, t_base = 0, t_pc = 0, t_oc = 1, t_e0 = 0, t_e1 = 0;
@@ -230,12 +240,7 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                 {
                     if (nvalid)
                     {
-                        nx_node = t_node;
-                        nx_misc = t_base | (t_pc << 8) | ((t_oc == 0 ? 1 : 0) << 16);
-                        nx_p0   = t_pc > 0 ? static_cast<int32_t>(g.pos[t_e0]) + 1 : 0;
-                        nx_p1   = t_pc > 1 ? static_cast<int32_t>(g.pos[t_e1]) + 1 : 0;
-                        nx_bs   = B.start(nrow);
-                        nx_bsp0 = B.start(nx_p0);
+                        pack_row(nrow, t_node, t_base, t_pc, t_oc, t_e0, t_e1);
                     }
                 }
             }
@@ -244,30 +249,23 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
 #endif
             const int32_t row  = r0 + k;
             const int32_t misc = __shfl_sync(kFull, cur_misc, k);
-            const int32_t p0   = __shfl_sync(kFull, cur_p0, k);
-            const int32_t bs   = __shfl_sync(kFull, cur_bs, k);
-            const int32_t bsp0 = __shfl_sync(kFull, cur_bsp0, k);
+            const int32_t w1   = __shfl_sync(kFull, cur_w1, k);
+            const int32_t w2   = __shfl_sync(kFull, cur_w2, k);
             const int32_t base = misc & 0xff;
             const int32_t pc   = (misc >> 8) & 0xff;
+            const int32_t bs   = ((misc >> 17) & 0x3fff) << 2;
+            const int32_t bsp0 = w1 & 0xffff;
             ring_slot          = (ring_slot + 1 == R) ? 0 : ring_slot + 1;
-            ScoreT* rowp       = B.row_ptr(row);
+            rowp += stride;
             ScoreT* srow       = ring + ring_slot * stride;
             int32_t* xchg      = s_xchg + (row & 1) * 16; // chunk-out values, double buffered by row parity
 
             int32_t local0, carry0;
             int32_t a0[kMaxChunksPerWarp], a1[kMaxChunksPerWarp], a2[kMaxChunksPerWarp], a3[kMaxChunksPerWarp];
-            const int32_t d0 = row - p0;
-            int32_t p1       = 0;
-            bool ring_row    = use_ring && pc <= 2 && d0 < R;
-            if (ring_row && pc == 2)
-            {
-                p1       = __shfl_sync(kFull, cur_p1, k);
-                ring_row = (row - p1) < R;
-            }
-            if (ring_row)
+            if (w2 & 0x10000)
             {
                 // ---- common case: at most two predecessors, both still in the shared-memory ring
-                int32_t sl0 = ring_slot - d0;
+                int32_t sl0 = ring_slot - (w2 & 0xff);
                 if (sl0 < 0)
                     sl0 += R;
                 const ScoreT* prow0 = ring + sl0 * stride;
@@ -276,11 +274,11 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                 int32_t bsp1 = 0, bep1 = -1;
                 if (pc == 2)
                 {
-                    int32_t sl1 = ring_slot - (row - p1);
+                    int32_t sl1 = ring_slot - ((w2 >> 8) & 0xff);
                     if (sl1 < 0)
                         sl1 += R;
                     prow1 = ring + sl1 * stride;
-                    bsp1  = B.start(p1);
+                    bsp1  = static_cast<int32_t>(static_cast<uint32_t>(w1) >> 16);
                     bep1  = min(bsp1 + band_width - kCPT, max_column);
                 }
                 int32_t first = 0;
@@ -345,7 +343,8 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
             {
                 // ---- general case: any number of predecessors, rows older than the ring come from global memory
                 const int32_t node_id = __shfl_sync(kFull, cur_node, k);
-                p1                    = __shfl_sync(kFull, cur_p1, k);
+                const int32_t p0      = __shfl_sync(kFull, cur_p0, k);
+                const int32_t p1      = __shfl_sync(kFull, cur_p1, k);
                 auto pred_row_ptr = [&](int32_t p) -> const ScoreT* {
                     const int32_t d = row - p;
                     if (use_ring && d < R)
@@ -437,28 +436,17 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
 #endif
 
             // ---- phase 2: carry into every chunk by a lane-wise max-plus scan over the chunk-out values, final values, stores
-            int32_t cin_lane;
-            {
-                int32_t v = (lane < nchunks) ? (xchg[lane] - (lane + 1) * G) : kNegInf;
-#pragma unroll
-                for (int32_t d = 1; d < 16; d <<= 1)
-                {
-                    const int32_t o = __shfl_up_sync(kFull, v, d);
-                    if (lane >= d)
-                        v = max(v, o);
-                }
-                int32_t excl = __shfl_up_sync(kFull, v, 1);
-                if (lane == 0)
-                    excl = kNegInf;
-                cin_lane = static_cast<ScoreT>(lane * G + max(carry0, excl)); // closed value of the cell left of chunk `lane`
-            }
+            // lane l < nchunks holds the closed out-value of chunk l rebased to column 0; the carry into chunk c is the maximum
+            // over the chunks to its left (one redux per owned chunk instead of a shuffle scan)
+            const int32_t xv = (lane < nchunks) ? (xchg[lane] - (lane + 1) * G) : kNegInf;
 #pragma unroll
             for (int32_t ci = 0; ci < kMaxChunksPerWarp; ci++)
             {
                 const int32_t c = warp + ci * nw_eff;
                 if (c < nchunks)
                 {
-                    const int32_t cin   = __shfl_sync(kFull, cin_lane, c);
+                    const int32_t xm    = __reduce_max_sync(kFull, lane < c ? xv : kNegInf);
+                    const int32_t cin   = static_cast<ScoreT>(c * G + max(carry0, xm)); // closed value of the cell left of chunk c
                     const int32_t cleft = (c == 0) ? local0 : cin;
                     const int32_t L     = cin + 4 * gap * lane;
                     const int32_t s0    = static_cast<ScoreT>(max(a0[ci], L + gap));
@@ -479,18 +467,18 @@ __device__ int32_t nw_banded_v2(const Win<SizeT>& g, int32_t graph_count, const 
                         *reinterpret_cast<Vec4<ScoreT>*>(srow + o) = out;
                     if (c == nchunks - 1)
                     {
-                        // last real cell (local band_width) + right padding
-                        const int32_t last = __shfl_sync(kFull, s3, 31);
-                        if (lane < 2)
+                        // last real cell (local band_width) + right padding: lane 31 holds the last cell
+                        if (lane >= 30)
                         {
                             Vec4<ScoreT> tl;
-                            tl.x = static_cast<ScoreT>(lane == 0 ? last : kMin);
+                            tl.x = static_cast<ScoreT>(lane == 31 ? s3 : kMin);
                             tl.y = static_cast<ScoreT>(kMin);
                             tl.z = static_cast<ScoreT>(kMin);
                             tl.w = static_cast<ScoreT>(kMin);
-                            *reinterpret_cast<Vec4<ScoreT>*>(rowp + band_width + 4 * lane) = tl;
+                            const int32_t to = band_width + 4 * (31 - lane);
+                            *reinterpret_cast<Vec4<ScoreT>*>(rowp + to) = tl;
                             if (use_ring)
-                                *reinterpret_cast<Vec4<ScoreT>*>(srow + band_width + 4 * lane) = tl;
+                                *reinterpret_cast<Vec4<ScoreT>*>(srow + to) = tl;
                         }
                     }
                 }
