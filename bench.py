@@ -296,7 +296,9 @@ def main():
     value = total_windows * args.steps / (dev_ms / 1e3)
 
     # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
-    h2d = int(((seq_len + 3) // 4 * 4).sum()) * 2 + 24 * n_win + 4 * len(seq_len)
+    # sequences (padded to 4 B per read) + window descriptors + read lengths; base weights are unit weights here and are
+    # set on the device (no host traffic)
+    h2d = int(((seq_len + 3) // 4 * 4).sum()) + 24 * n_win + 4 * len(seq_len)
     d2h = n_win * cfg.max_consensus_size * 3 + n_win * 20
     for _ in range(max(1, min(args.warmup, 2))):
         batch.reset()

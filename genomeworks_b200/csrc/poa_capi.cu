@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gwb200;
@@ -77,6 +78,14 @@ struct gwb200_poa_batch
     uint8_t* h_block = nullptr;
     uint8_t* h_sequences = nullptr;
     int8_t* h_weights = nullptr;
+    bool weights_present = false; // false: every read so far had unit base weights (h_weights is not filled, the device array is memset)
+    struct CopyJob
+    {
+        uint8_t* dst;
+        const char* src;
+        int32_t len;
+    };
+    std::vector<CopyJob>* deferred = nullptr; // set by add_groups_flat: sequence copies are collected and run on several threads
     int32_t* h_seq_lengths = nullptr;
     WindowInfo* h_windows = nullptr;
     uint8_t* h_consensus = nullptr;
@@ -653,6 +662,7 @@ int gwb200_poa_batch_reset(gwb200_poa_batch* b)
     b->global_sequence_idx    = 0;
     b->next_scores_offset     = 0;
     b->avail_buf_mem          = b->scorebuf_alloc_size;
+    b->weights_present        = false;
     b->launched               = false;
     b->results_on_host        = false;
     return 0;
@@ -734,11 +744,25 @@ int gwb200_poa_batch_add_group(gwb200_poa_batch* b, int32_t n, const char* const
                 else
                 {
                     w->num_seqs++;
-                    std::memcpy(b->h_sequences + b->num_nucleotides_copied, seqs[i], len);
-                    if (wt == nullptr)
-                        std::memset(b->h_weights + b->num_nucleotides_copied, 1, len);
+                    if (b->deferred)
+                        b->deferred->push_back({b->h_sequences + b->num_nucleotides_copied, seqs[i], len});
                     else
+                        std::memcpy(b->h_sequences + b->num_nucleotides_copied, seqs[i], len);
+                    if (wt == nullptr)
+                    {
+                        if (b->weights_present)
+                            std::memset(b->h_weights + b->num_nucleotides_copied, 1, len);
+                    }
+                    else
+                    {
+                        if (!b->weights_present)
+                        {
+                            // first weighted read of this batch: the reads before it carry unit weights (cudapoa_batch.cuh:519-527)
+                            std::memset(b->h_weights, 1, b->num_nucleotides_copied);
+                            b->weights_present = true;
+                        }
                         std::memcpy(b->h_weights + b->num_nucleotides_copied, wt, len);
+                    }
                     b->h_seq_lengths[b->global_sequence_idx] = len;
                     b->num_nucleotides_copied += align_up(len, 4);
                     b->global_sequence_idx++;
@@ -768,6 +792,41 @@ int gwb200_poa_batch_add_groups_flat(gwb200_poa_batch* b, int32_t n_windows, con
     std::vector<const int8_t*> wts;
     int64_t off = 0;
     int32_t si  = 0;
+    // the sequence bytes are copied into the pinned staging buffer by several threads after the (serial) bookkeeping
+    std::vector<gwb200_poa_batch::CopyJob> jobs;
+    struct Flush
+    {
+        gwb200_poa_batch* b;
+        std::vector<gwb200_poa_batch::CopyJob>& jobs;
+        ~Flush()
+        {
+            b->deferred = nullptr;
+            int64_t total = 0;
+            for (const auto& j : jobs)
+                total += j.len;
+            const int32_t nt = static_cast<int32_t>(std::min<int64_t>(std::min<int64_t>(16, std::max(1u, std::thread::hardware_concurrency())), total / (4 << 20) + 1));
+            auto run = [&](size_t lo, size_t hi) {
+                for (size_t k = lo; k < hi; k++)
+                    std::memcpy(jobs[k].dst, jobs[k].src, jobs[k].len);
+            };
+            if (nt <= 1)
+            {
+                run(0, jobs.size());
+                return;
+            }
+            std::vector<std::thread> th;
+            const size_t per = (jobs.size() + nt - 1) / nt;
+            for (int32_t t = 0; t < nt; t++)
+            {
+                const size_t lo = std::min(jobs.size(), per * t), hi = std::min(jobs.size(), per * (t + 1));
+                if (lo < hi)
+                    th.emplace_back(run, lo, hi);
+            }
+            for (auto& t : th)
+                t.join();
+        }
+    } flush{b, jobs};
+    b->deferred = &jobs;
     for (int32_t w = 0; w < n_windows; w++)
     {
         const int32_t ns = win_nseq[w];
@@ -805,7 +864,10 @@ int gwb200_poa_batch_upload(gwb200_poa_batch* b)
     DeviceGuard guard(b->device_id);
     // cudapoa_batch.cuh:171-178
     GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(b->P.sequences), b->h_sequences, b->num_nucleotides_copied, cudaMemcpyHostToDevice, b->stream));
-    GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<int8_t*>(b->P.weights), b->h_weights, b->num_nucleotides_copied, cudaMemcpyHostToDevice, b->stream));
+    if (b->weights_present)
+        GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<int8_t*>(b->P.weights), b->h_weights, b->num_nucleotides_copied, cudaMemcpyHostToDevice, b->stream));
+    else
+        GWB200_CUDA_TRY(cudaMemsetAsync(const_cast<int8_t*>(b->P.weights), 1, b->num_nucleotides_copied, b->stream)); // unit weights: no host traffic
     GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<WindowInfo*>(b->P.windows), b->h_windows, sizeof(WindowInfo) * b->poa_count, cudaMemcpyHostToDevice, b->stream));
     GWB200_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(b->P.seq_lengths), b->h_seq_lengths, sizeof(int32_t) * b->global_sequence_idx, cudaMemcpyHostToDevice, b->stream));
     return 0;

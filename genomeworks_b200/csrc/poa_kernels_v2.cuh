@@ -978,12 +978,15 @@ __device__ int32_t add_alignment_v2(const Win<SizeT>& g, int32_t& node_count_io,
 
 // topologicalSortDeviceUtil (cudapoa_topsort.cuh:45-97): same Kahn FIFO order. The in-degree counters (u8) and a 64-entry
 // tagged window of the FIFO live in the shared-memory pool; a compressed "only child" word per node (SizeT wide) lives in the
-// pool too when it fits and in a global scratch array otherwise (chains run along consecutive node ids, so those loads hit L1).
+// pool too as far as it fits, the words of the remaining (highest) node ids in a global scratch array (chains run along
+// consecutive node ids, so those loads hit L1).
 // Both are filled by coalesced loads; the serial walk touches the adjacency arrays only at branching nodes and global memory
 // otherwise only to write sorted[] / pos[].
 template <typename SizeT, typename WordT>
-__device__ void topsort_walk(const Win<SizeT>& g, int32_t node_count, int32_t* q_tag, int32_t* q_node, uint8_t* cnt, WordT* e0w)
+__device__ void topsort_walk(const Win<SizeT>& g, int32_t node_count, int32_t* q_tag, int32_t* q_node, uint8_t* cnt, WordT* e0s,
+                             int32_t n_shared, WordT* e0g)
 {
+    // child word of node n: e0s[n] (shared memory) for n < n_shared, e0g[n] (global scratch) otherwise
     const int32_t lane     = threadIdx.x & 31;
     constexpr int32_t kQ   = 64;
     constexpr WordT kOne   = static_cast<WordT>(1) << (8 * sizeof(WordT) - 1); // flag: exactly one out edge
@@ -1004,7 +1007,11 @@ __device__ void topsort_walk(const Win<SizeT>& g, int32_t node_count, int32_t* q
             const int32_t oc = g.out_cnt[n];
             const WordT e0   = static_cast<WordT>(static_cast<WordT>(g.out_edge(n, 0)) & kNone);
             cnt[n]           = static_cast<uint8_t>(c);
-            e0w[n]           = static_cast<WordT>(oc == 0 ? kNone : (oc == 1 ? (kOne | e0) : e0));
+            const WordT wv   = static_cast<WordT>(oc == 0 ? kNone : (oc == 1 ? (kOne | e0) : e0));
+            if (n < n_shared)
+                e0s[n] = wv;
+            else
+                e0g[n] = wv;
         }
         const bool is_src = n < node_count && c == 0;
         const uint32_t m  = __ballot_sync(kFull, is_src);
@@ -1035,7 +1042,7 @@ __device__ void topsort_walk(const Win<SizeT>& g, int32_t node_count, int32_t* q
                 node               = (q_tag[slot] == n) ? q_node[slot] : static_cast<int32_t>(g.sorted[n]);
             }
             reg_node      = -1;
-            const WordT w = e0w[node];
+            const WordT w = node < n_shared ? e0s[node] : e0g[node];
             n++;
             if (w & kOne)
             {
@@ -1101,13 +1108,12 @@ __device__ void topsort_v2(const Win<SizeT>& g, int32_t node_count, uint8_t* poo
     int32_t* q_tag       = reinterpret_cast<int32_t*>(pool);
     int32_t* q_node      = q_tag + kQ;
     uint8_t* cnt         = pool + kQ * 8;
-    if (fixed + static_cast<int32_t>(sizeof(WordT)) * node_count <= pool_bytes)
+    if (fixed <= pool_bytes)
     {
-        topsort_walk<SizeT, WordT>(g, node_count, q_tag, q_node, cnt, reinterpret_cast<WordT*>(pool + kQ * 8 + nc4));
-    }
-    else if (fixed <= pool_bytes)
-    {
-        topsort_walk<SizeT, WordT>(g, node_count, q_tag, q_node, cnt, static_cast<WordT*>(scratch));
+        // as many child words as fit stay in shared memory (low node ids: the first read's backbone), the rest go to `scratch`
+        const int32_t n_shared = min(node_count, (pool_bytes - fixed) / static_cast<int32_t>(sizeof(WordT)));
+        topsort_walk<SizeT, WordT>(g, node_count, q_tag, q_node, cnt, reinterpret_cast<WordT*>(pool + kQ * 8 + nc4), n_shared,
+                                   static_cast<WordT*>(scratch));
     }
     else
     {
