@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
     ap.add_argument("--windows", type=int, default=0, help="windows (or pairs) per GPU per step")
+    ap.add_argument("--factor", type=float, default=0.0, help="override adaptive_storage_factor of the workload (C3 default 3.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gpu-reference", action="store_true", help="also time the reference CUDA kernels (oracle/_ref) on rank 0")
     args = ap.parse_args()
@@ -243,6 +244,9 @@ def main():
         return
 
     from genomeworks_b200 import cudapoa, synth
+    if args.factor > 0:
+        wp["factor"] = args.factor
+        wp["name"] = wp["name"].replace("adaptive_storage_factor 3.0", "adaptive_storage_factor %g" % args.factor)
     cfg = cudapoa.make_config(wp["max_seq"], wp["reads"], wp["band"], wp["band_mode"], adaptive_storage_factor=wp["factor"])
     stream = torch.cuda.Stream()
     free_b, _ = torch.cuda.mem_get_info()

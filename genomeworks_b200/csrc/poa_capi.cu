@@ -101,6 +101,8 @@ struct gwb200_poa_batch
     DeviceParams P{};
     V2Extra X{};
     bool use_v2 = true;
+    bool tb_mode = false;    // static_band_traceback / adaptive_band_traceback
+    int32_t trace_bytes = 2; // sizeof(TraceT): 1 unless max_banded_pred_distance > 127 (cudapoa_limits.hpp:56-60)
     int32_t nw_override = 0;
     bool timers_on = false;
     unsigned long long* d_timers = nullptr;
@@ -123,7 +125,7 @@ struct Sizes
     int32_t aln_capacity = 0, stack_capacity = 0;
 };
 
-Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz, bool msa)
+Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz, bool msa, bool tb = false, int32_t trace_bytes = 2)
 {
     Sizes s;
     const int64_t mn = c.max_nodes_per_graph;
@@ -156,8 +158,11 @@ Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz,
     d += (align_up(std::max(c.max_sequence_size, 1), 4) + 8ll) * sz; // v2 read -> node map
     d += 64;                                             // phase timers
     d += 256 * 36; // carving alignment slack
+    if (tb)
+        d += static_cast<int64_t>(c.matrix_sequence_dimension) * c.max_banded_pred_distance * score_bytes + 256; // score ring (allocate_block.hpp:333-334,374)
     s.dev_per_poa    = d;
-    s.dev_per_matrix = static_cast<int64_t>(c.matrix_sequence_dimension) * mn * score_bytes;
+    // the pooled matrix: scores, or the trace matrix in the traceback modes (allocate_block.hpp:76-84)
+    s.dev_per_matrix = static_cast<int64_t>(c.matrix_sequence_dimension) * mn * (tb ? trace_bytes : score_bytes);
     int64_t h        = s.seq_bytes_per_poa * 2 + 4ll * c.max_sequences_per_poa + sizeof(WindowInfo) + c.max_consensus_size * 3ll + 4 * 3 + 8;
     if (msa)
         h += static_cast<int64_t>(c.max_sequences_per_poa) * c.max_consensus_size;
@@ -172,6 +177,8 @@ struct V2Choice
 };
 V2Choice choose_v2(const gwb200_poa_batch* b)
 {
+    if (b->tb_mode)
+        return {1, 1}; // the traceback-matrix alignment is a one-warp routine (poa_kernels_tb.cuh)
     // warps per window: one per 128-column band chunk, at most 4; chunks per warp bounded by the widest band the mode can
     // reach (adaptive bands grow up to 1536 = 12 chunks)
     const bool adaptive   = b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND && b->cfg.alignment_band_width < kMaxAdaptiveBW;
@@ -466,8 +473,6 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
         return set_error(GWB200_E_INVALID_ARGUMENT, "max_gpu_mem has to be either -1 (=all available GPU memory) or greater or equal than 0.");
     if (int rc = validate_config(*cfg))
         return rc;
-    if (cfg->band_mode == GWB200_POA_STATIC_BAND_TRACEBACK || cfg->band_mode == GWB200_POA_ADAPTIVE_BAND_TRACEBACK)
-        return set_error(GWB200_E_RUNTIME, "traceback band modes are not implemented by this engine yet (no fallback exists)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device_id)
     {
@@ -489,6 +494,13 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     b->score_bytes      = b->score32 ? 4 : 2;
     b->size_bytes       = b->size32 ? 4 : 2;
     b->msa              = (output_mask & GWB200_POA_OUTPUT_MSA) != 0;
+    b->tb_mode          = cfg->band_mode == GWB200_POA_STATIC_BAND_TRACEBACK || cfg->band_mode == GWB200_POA_ADAPTIVE_BAND_TRACEBACK;
+    b->trace_bytes      = cfg->max_banded_pred_distance > INT8_MAX ? 2 : 1;
+    if (b->tb_mode && cfg->max_banded_pred_distance < 1)
+    {
+        delete b;
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_banded_pred_distance has to be positive in the traceback band modes");
+    }
     b->bid              = gwb200_poa_batch::batches++;
     {
         const char* nwv = std::getenv("GWB200_POA_WARPS"); // development switch: warps per window (1, 2 or 4)
@@ -504,7 +516,7 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     int64_t avail = static_cast<int64_t>(static_cast<double>(free_b) * 0.95);
     if (max_gpu_mem >= 0)
         avail = std::min(avail, max_gpu_mem);
-    const Sizes sz = compute_sizes(*cfg, b->score_bytes, b->size_bytes, b->msa);
+    const Sizes sz = compute_sizes(*cfg, b->score_bytes, b->size_bytes, b->msa, b->tb_mode, b->trace_bytes);
     if (avail < sz.dev_per_poa + (cfg->band_mode == GWB200_POA_FULL_BAND ? 0 : sz.dev_per_matrix) || sz.dev_per_poa + sz.dev_per_matrix <= 0)
     {
         std::string msg = "Requires at least " + std::to_string(sz.dev_per_poa + sz.dev_per_matrix) +
@@ -604,10 +616,23 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
         b->d_timers      = dc.take<unsigned long long>(n * 8);
         b->X.timers      = nullptr;
         b->X.pool_bytes  = v2_pool_bytes(b);
+        b->X.tb_scores   = nullptr;
+        b->X.tb_trace    = nullptr;
+        b->X.tb_height   = cfg->max_banded_pred_distance;
+        b->X.tb_trace16  = b->trace_bytes == 2 ? 1 : 0;
+        if (b->tb_mode)
+            b->X.tb_scores = dc.take<uint8_t>(n * (static_cast<int64_t>(cfg->matrix_sequence_dimension) * cfg->max_banded_pred_distance * b->score_bytes + 256));
         // everything that is left is the score pool (allocate_block.hpp:227-239)
         dc.off                 = align_up64(dc.off, 256);
         P.scores               = b->d_block + dc.off;
         b->scorebuf_alloc_size = total_d - dc.off;
+        if (b->tb_mode)
+        {
+            // in the traceback modes the pooled remainder is the trace matrix (allocate_block.hpp:236-239); cells the walk may
+            // read without a prior write (row 0, unreachable boundary cells) are defined as zero
+            b->X.tb_trace = P.scores;
+            cudaMemsetAsync(P.scores, 0, b->scorebuf_alloc_size, b->stream);
+        }
         P.max_nodes            = cfg->max_nodes_per_graph;
         P.matrix_seq_dim       = cfg->matrix_sequence_dimension;
         P.max_consensus        = cfg->max_consensus_size;
@@ -629,6 +654,8 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
             // the v2 kernel packs band starts in 15 bits (x4) and needs its staged read plus a few score rows in shared memory
             if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || b->X.pool_bytes > 200 * 1024)
                 b->use_v2 = false; // first-generation kernel
+            if (b->tb_mode)
+                b->use_v2 = true; // only the v2 kernel family hosts the traceback-matrix alignment
         }
     }
     gwb200_poa_batch_reset(b);
@@ -685,7 +712,7 @@ int gwb200_poa_batch_add_group(gwb200_poa_batch* b, int32_t n, const char* const
     // reserve_buf
     {
         const int64_t width = (c.band_mode != GWB200_POA_FULL_BAND) ? c.matrix_sequence_dimension : align_up(max_seq_length + 1 + kCPT, 4);
-        const int64_t req   = width * static_cast<int64_t>(c.max_nodes_per_graph) * b->score_bytes;
+        const int64_t req   = width * static_cast<int64_t>(c.max_nodes_per_graph) * (b->tb_mode ? b->trace_bytes : b->score_bytes); // cudapoa_batch.cuh:551-553
         if (req > b->avail_buf_mem)
             return GWB200_POA_EXCEEDED_MAXIMUM_POAS;
         b->avail_buf_mem -= req;

@@ -35,6 +35,7 @@ enum Status : int32_t
     st_node_count_exceeded_maximum_graph_size = 4,
     st_edge_count_exceeded_maximum_graph_size = 5,
     st_exceeded_adaptive_banded_matrix_size   = 6,
+    st_exceeded_maximum_predecessor_distance  = 7,
     st_loop_count_exceeded_upper_bound        = 8,
     st_exceeded_maximum_sequence_size         = 2,
     st_generic_error                          = 12

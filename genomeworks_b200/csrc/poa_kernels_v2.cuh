@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "poa_kernels.cuh"
+#include "poa_kernels_tb.cuh"
 
 namespace gwb200
 {
@@ -36,6 +37,12 @@ struct V2Extra
     void* rd_node;      // SizeT [n_windows][max_seq_aligned] : graph node aligned to each read base (-1 = insertion)
     int32_t rd_capacity;
     int32_t pool_bytes; // dynamic shared memory per CTA
+    // traceback band modes (poa_kernels_tb.cuh): score ring [n_windows][max_pred_distance][matrix_seq_dim] ScoreT and the trace
+    // matrix [n_windows][max_nodes][matrix_seq_dim] TraceT (int8 unless max_pred_distance > 127)
+    void* tb_scores;
+    void* tb_trace;
+    int32_t tb_height;
+    int32_t tb_trace16;
     unsigned long long* timers; // optional [n_windows][8] phase cycle counters (nullptr = off)
 };
 
@@ -1220,7 +1227,38 @@ __global__ void __launch_bounds__(32 * NW, (NW == 4 ? GWB200_POA_NW4_BLOCKS : (N
             break;
         }
         int32_t alen;
-        if (P.band_mode != bm_full_band)
+        if (P.band_mode == bm_static_band_traceback || P.band_mode == bm_adaptive_band_traceback)
+        {
+            // cudapoa_kernels.cuh:270-346; served by the one-warp kernel only (the host selects it)
+            alen = kNWBacktrackFail;
+            if constexpr (NW == 1 && MAXC == 1)
+            {
+                const bool adaptive = (P.band_mode == bm_adaptive_band_traceback && P.band_width < kMaxAdaptiveBW);
+                ScoreT* tb_scores   = static_cast<ScoreT*>(X.tb_scores) + static_cast<int64_t>(w) * X.tb_height * P.matrix_seq_dim;
+                const int64_t toff  = static_cast<int64_t>(banded_buffer_size) * static_cast<int64_t>(w);
+                int32_t rerun       = 0;
+                for (int32_t attempt = 0; attempt < 2; attempt++)
+                {
+                    if (X.tb_trace16)
+                        alen = nw_banded_tb<ScoreT, SizeT, int16_t>(g, node_count, sequence, seq_len, tb_scores, static_cast<int16_t*>(X.tb_trace) + toff,
+                                                                    banded_buffer_size, aln_graph, aln_read, P.band_width, X.tb_height, P.gap,
+                                                                    P.mismatch, P.match, rerun, adaptive, cells);
+                    else
+                        alen = nw_banded_tb<ScoreT, SizeT, int8_t>(g, node_count, sequence, seq_len, tb_scores, static_cast<int8_t*>(X.tb_trace) + toff,
+                                                                   banded_buffer_size, aln_graph, aln_read, P.band_width, X.tb_height, P.gap,
+                                                                   P.mismatch, P.match, rerun, adaptive, cells);
+                    if (!adaptive || attempt == 1 || !(alen == kShiftLeft || alen == kShiftRight))
+                        break;
+                    rerun = alen;
+                }
+            }
+            if (alen == kNWTracebackBufferFail)
+            {
+                error = st_exceeded_maximum_predecessor_distance;
+                break;
+            }
+        }
+        else if (P.band_mode != bm_full_band)
         {
             const bool adaptive = (P.band_mode == bm_adaptive_band && P.band_width < kMaxAdaptiveBW);
             int32_t rerun       = 0;

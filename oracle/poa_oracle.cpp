@@ -39,6 +39,7 @@ constexpr int32_t SHIFT_LEFT     = -10;
 constexpr int32_t SHIFT_RIGHT    = -11;
 constexpr int32_t NW_BACKTRACK_FAILED = -1;
 constexpr int32_t NW_ADAPTIVE_STORAGE_FAILED = -2;
+constexpr int32_t NW_TRACEBACK_BUFFER_FAILED = -3; // CUDAPOA_KERNEL_NW_TRACEBACK_BUFFER_FAILED cudapoa_structs.cuh:55
 
 // cudapoa.hpp:34-49
 enum Status : int32_t
@@ -708,6 +709,321 @@ int32_t nw_banded(Graph& g, int32_t graph_count, const uint8_t* read, int32_t re
 }
 
 // needlemanWunsch (full band) -- cudapoa_nw.cuh:149-454. Columns beyond read_length inside the last 4-cell group are
+// ---------------------------------------------------------------------------------------------------------
+// Banded NW with traceback matrix -- cudapoa_nw_tb_banded.cuh. The score matrix is kept only for the last
+// `score_matrix_height` rows (row % height), the move of every cell goes to a full-height trace matrix:
+// 0 = horizontal, +d = diagonal to the row d above, -d = vertical to the row d above.
+template <typename ScoreT, typename TraceT>
+struct TbCtx
+{
+    ScoreBuf<ScoreT>* sb;          // [score_matrix_height][bw + PAD]
+    std::vector<TraceT>* tb;       // [max_nodes][bw + PAD], persistent per window like the device buffer (zero-initialised)
+    int32_t bw, band_shift, max_column, height;
+    float gradient;
+    ScoreT min_score;
+    int64_t stride() const { return static_cast<int64_t>(bw + PAD); }
+    // set_score_tb -- :46-67 (column == -1 quirk: offset band_start)
+    void set_score(int32_t row, int32_t column, int32_t value, int32_t band_start)
+    {
+        int32_t c = (column == -1) ? band_start : column - band_start;
+        row       = row % height;
+        sb->wr(static_cast<int64_t>(c) + static_cast<int64_t>(row) * stride(), value);
+    }
+    // get_score_tb -- :111-138
+    ScoreT get_score(int32_t row, int32_t column)
+    {
+        int32_t bs = band_start_for_row(row, gradient, bw, band_shift, max_column);
+        int32_t be = std::min(bs + bw, max_column);
+        if ((column > be || column < bs) && column != -1)
+            return min_score;
+        int32_t c = (column == -1) ? 0 : column - bs;
+        return sb->rd(static_cast<int64_t>(c) + static_cast<int64_t>(row % height) * stride());
+    }
+    // initialize_band_tb -- :83-101 (band_end from the unclamped band_start, offsets from max(1, band_start))
+    void initialize_band(int32_t row, int32_t band_start)
+    {
+        int32_t band_end = band_start + bw;
+        int32_t bs       = std::max(1, band_start);
+        set_score(row, bs, min_score, bs);
+        for (int32_t lane = 0; lane < PAD; lane++)
+            set_score(row, lane + band_end, min_score, bs);
+    }
+    void tb_wr(int64_t i, int32_t v)
+    {
+        if (i >= 0 && i < static_cast<int64_t>(tb->size()))
+            (*tb)[i] = static_cast<TraceT>(v); // truncation on store
+    }
+    int32_t tb_rd(int64_t i) const { return (i >= 0 && i < static_cast<int64_t>(tb->size())) ? static_cast<int32_t>((*tb)[i]) : 0; }
+    // get_scores_tb -- :140-262: one predecessor's contribution to four cells and their moves
+    void get_scores(int32_t pred_node, int32_t current_node, int32_t column, int32_t gap, const int32_t prof[4], ScoreT score[4], TraceT trace[4])
+    {
+        int32_t bs = band_start_for_row(pred_node, gradient, bw, band_shift, max_column);
+        int32_t be = std::min(bs + bw - CPT, max_column);
+        if ((column > be || column < bs) && column != -1)
+            return;
+        int32_t c  = (column == -1) ? 0 : column - bs;
+        int64_t p  = static_cast<int64_t>(c) + static_cast<int64_t>(pred_node % height) * stride();
+        ScoreT a[5] = {sb->rd(p), sb->rd(p + 1), sb->rd(p + 2), sb->rd(p + 3), sb->rd(p + 4)};
+        for (int32_t k = 0; k < 4; k++)
+        {
+            const int32_t diag = a[k] + prof[k];
+            const int32_t vert = a[k + 1] + gap;
+            if (diag >= vert)
+            {
+                if (diag > score[k])
+                {
+                    score[k] = static_cast<ScoreT>(diag);
+                    trace[k] = static_cast<TraceT>(current_node - pred_node);
+                }
+            }
+            else
+            {
+                if (vert > score[k])
+                {
+                    score[k] = static_cast<ScoreT>(vert);
+                    trace[k] = static_cast<TraceT>(-(current_node - pred_node));
+                }
+            }
+        }
+    }
+};
+
+// needlemanWunschBandedTraceback -- cudapoa_nw_tb_banded.cuh:264-643
+template <typename ScoreT, typename TraceT>
+int32_t nw_banded_tb(Graph& g, int32_t graph_count, const uint8_t* read, int32_t read_length, ScoreBuf<ScoreT>& sb, std::vector<TraceT>& tbuf,
+                     float max_buffer_size, int32_t* alignment_graph, int32_t* alignment_read, int32_t band_width, int32_t score_matrix_height,
+                     int32_t gap, int32_t mismatch, int32_t match, int32_t rerun, bool adaptive, int64_t* cells_out)
+{
+    const ScoreT min_score = std::numeric_limits<ScoreT>::min() / 2;
+    float gradient         = g_fdiv(static_cast<float>(read_length + 1), static_cast<float>(graph_count + 1));
+    int32_t max_column     = read_length + 1;
+    int32_t band_shift     = band_width / 2;
+    if (adaptive)
+    {
+        if (rerun == SHIFT_LEFT && band_width <= MAX_ADAPTIVE_BW / 2)
+        {
+            band_width *= 2;
+            band_shift = static_cast<int32_t>(band_shift * 2.5);
+        }
+        if (rerun == SHIFT_RIGHT && band_width <= MAX_ADAPTIVE_BW / 2)
+        {
+            band_width *= 2;
+            band_shift = static_cast<int32_t>(band_shift * 1.5);
+        }
+        float required = static_cast<float>(graph_count) * static_cast<float>(band_width + PAD);
+        if (required > max_buffer_size)
+            return NW_ADAPTIVE_STORAGE_FAILED;
+    }
+    if (cells_out)
+        *cells_out += static_cast<int64_t>(graph_count) * band_width;
+
+    TbCtx<ScoreT, TraceT> c{&sb, &tbuf, band_width, band_shift, max_column, score_matrix_height, gradient, min_score};
+    const int64_t stride = c.stride();
+
+    for (int32_t j = 0; j < band_width + PAD; j++)
+        c.set_score(0, j, j * gap, 0);
+
+    for (int32_t graph_pos = 0; graph_pos < graph_count; graph_pos++)
+    {
+        int32_t node_id      = g.sorted[graph_pos];
+        int32_t score_gIdx   = graph_pos + 1;
+        int32_t band_start   = band_start_for_row(score_gIdx, gradient, band_width, band_shift, max_column);
+        int32_t pred_node_id = g.in_edges[node_id * MAXE];
+        c.initialize_band(score_gIdx, band_start);
+
+        int32_t first_element_prev_score = 0;
+        uint16_t pred_count              = g.in_cnt[node_id];
+        int32_t pred_idx                 = 0;
+        {
+            // vertical boundary, lane 0 (:361-441)
+            int32_t penalty;
+            if (pred_count == 0)
+            {
+                sb.wr(static_cast<int64_t>(score_gIdx % score_matrix_height) * stride, gap);
+                c.tb_wr(static_cast<int64_t>(score_gIdx) * stride, -score_gIdx);
+            }
+            else
+            {
+                const int64_t index = static_cast<int64_t>(score_gIdx) * stride;
+                pred_idx            = g.pos[pred_node_id] + 1;
+                if ((graph_pos - pred_idx) < score_matrix_height)
+                {
+                    c.tb_wr(index, -(score_gIdx - pred_idx));
+                    if (band_start > CPT && pred_count == 1)
+                    {
+                        first_element_prev_score = min_score + gap;
+                    }
+                    else
+                    {
+                        penalty = std::max<int32_t>(min_score, c.get_score(pred_idx, -1));
+                        for (int32_t p = 1; p < pred_count; p++)
+                        {
+                            int32_t pred_idx_tmp = g.pos[g.in_edges[node_id * MAXE + p]] + 1;
+                            if ((score_gIdx - pred_idx_tmp) < score_matrix_height)
+                            {
+                                int32_t score_tmp = c.get_score(pred_idx_tmp, -1);
+                                if (penalty < score_tmp)
+                                {
+                                    penalty = score_tmp;
+                                    c.tb_wr(index, -(score_gIdx - pred_idx_tmp));
+                                }
+                            }
+                        }
+                        first_element_prev_score = penalty + gap;
+                        c.set_score(score_gIdx, -1, first_element_prev_score, band_start);
+                    }
+                }
+                else
+                {
+                    penalty = min_score;
+                    for (int32_t p = 1; p < pred_count; p++)
+                    {
+                        int32_t pred_idx_tmp = g.pos[g.in_edges[node_id * MAXE + p]] + 1;
+                        if ((score_gIdx - pred_idx_tmp) < score_matrix_height)
+                        {
+                            int32_t score_tmp = c.get_score(pred_idx_tmp, -1);
+                            if (penalty < score_tmp)
+                            {
+                                penalty = score_tmp;
+                                c.tb_wr(index, -(score_gIdx - pred_idx_tmp));
+                            }
+                        }
+                    }
+                    first_element_prev_score = penalty + gap;
+                    c.set_score(score_gIdx, -1, first_element_prev_score, band_start);
+                }
+            }
+        }
+        const uint8_t graph_base = g.nodes[node_id];
+
+        // chunks of 128 columns; within a chunk the warp's 32 lanes x 4 cells, horizontal closure to its fixpoint (:448-546)
+        for (int32_t chunk_start = band_start; chunk_start < band_start + band_width; chunk_start += MIN_BW)
+        {
+            ScoreT sc[MIN_BW];
+            TraceT tr[MIN_BW];
+            for (int32_t lane = 0; lane < 32; lane++)
+            {
+                int32_t read_pos = chunk_start + lane * CPT;
+                int32_t prof[4];
+                for (int32_t k = 0; k < 4; k++)
+                {
+                    // bytes past the end of the read only reach cells with column > read_length (see nw_banded)
+                    uint8_t rb = (read_pos + k < read_length) ? read[read_pos + k] : 0;
+                    prof[k]    = (graph_base == rb) ? match : mismatch;
+                }
+                ScoreT s4[4] = {min_score, min_score, min_score, min_score};
+                TraceT t4[4] = {0, 0, 0, 0}; // uninitialised on the device; only cells no predecessor reaches keep it
+                c.get_scores(pred_idx, score_gIdx, read_pos, gap, prof, s4, t4); // predecessor 0: no distance test (as the reference)
+                for (int32_t p = 1; p < pred_count; p++)
+                {
+                    int32_t pred_idx_tmp = g.pos[g.in_edges[node_id * MAXE + p]] + 1;
+                    if ((score_gIdx - pred_idx_tmp) < score_matrix_height)
+                        c.get_scores(pred_idx_tmp, score_gIdx, read_pos, gap, prof, s4, t4);
+                }
+                for (int32_t k = 0; k < 4; k++)
+                {
+                    sc[lane * 4 + k] = s4[k];
+                    tr[lane * 4 + k] = t4[k];
+                }
+            }
+            // the relaxation loop's fixpoint: left-to-right closure; a cell's move becomes 0 iff the horizontal value is strictly
+            // larger than what the predecessors gave (every update in the loop is strict and monotone)
+            int32_t left = first_element_prev_score;
+            for (int32_t k = 0; k < MIN_BW; k++)
+            {
+                if (sc[k] < left + gap)
+                {
+                    sc[k] = static_cast<ScoreT>(left + gap);
+                    tr[k] = 0;
+                }
+                left = sc[k];
+            }
+            first_element_prev_score = sc[MIN_BW - 1];
+            for (int32_t k = 0; k < MIN_BW; k++)
+            {
+                int64_t local = static_cast<int64_t>(chunk_start + k + 1 - band_start);
+                sb.wr(local + static_cast<int64_t>(score_gIdx % score_matrix_height) * stride, sc[k]);
+                c.tb_wr(local + static_cast<int64_t>(score_gIdx) * stride, tr[k]);
+            }
+        }
+    }
+
+    // end cell among sinks within the stored score rows (:553-579)
+    int32_t aligned_nodes = 0;
+    int32_t i = 0, j = read_length;
+    int32_t mscore = min_score;
+    for (int32_t idx = 1; idx <= graph_count; idx++)
+    {
+        if (g.out_cnt[g.sorted[idx - 1]] == 0)
+        {
+            if ((graph_count - idx) < score_matrix_height)
+            {
+                int32_t s = c.get_score(idx, j);
+                if (mscore < s)
+                {
+                    mscore = s;
+                    i      = idx;
+                }
+            }
+        }
+    }
+    if (i == 0)
+    {
+        j             = 0;
+        aligned_nodes = NW_TRACEBACK_BUFFER_FAILED;
+    }
+    // traceback over the trace matrix (:581-641)
+    int32_t loop_count = 0;
+    const int32_t limit = read_length + graph_count + 2;
+    while (!(i == 0 && j == 0) && loop_count < limit)
+    {
+        loop_count++;
+        int32_t band_start = band_start_for_row(i, gradient, band_width, band_shift, max_column);
+        int32_t trace      = c.tb_rd(static_cast<int64_t>(j - band_start) + static_cast<int64_t>(i) * stride);
+        if (trace == 0)
+        {
+            alignment_graph[aligned_nodes] = -1;
+            alignment_read[aligned_nodes]  = j - 1;
+            j--;
+        }
+        else if (trace < 0)
+        {
+            alignment_graph[aligned_nodes] = g.sorted[i - 1];
+            alignment_read[aligned_nodes]  = -1;
+            i += trace;
+        }
+        else
+        {
+            alignment_graph[aligned_nodes] = g.sorted[i - 1];
+            alignment_read[aligned_nodes]  = j - 1;
+            i -= trace;
+            j--;
+            if (adaptive && rerun == 0 && band_width < MAX_ADAPTIVE_BW)
+            {
+                int32_t threshold = std::max(1, max_column / 1024);
+                if (j > threshold && j < max_column - threshold)
+                {
+                    int32_t bs = band_start_for_row(i, gradient, band_width, band_shift, max_column);
+                    if (j <= bs + threshold)
+                    {
+                        aligned_nodes = SHIFT_LEFT;
+                        break;
+                    }
+                    if (j >= (bs + band_width - threshold))
+                    {
+                        aligned_nodes = SHIFT_RIGHT;
+                        break;
+                    }
+                }
+            }
+        }
+        aligned_nodes++;
+    }
+    if (loop_count >= limit)
+        aligned_nodes = NW_BACKTRACK_FAILED;
+    return aligned_nodes;
+}
+
 // computed from out-of-read bytes on the device; they never influence columns <= read_length and are not restated.
 template <typename ScoreT>
 int32_t nw_full(Graph& g, int32_t graph_count, const uint8_t* read, int32_t read_length, ScoreBuf<ScoreT>& sb,
@@ -1127,6 +1443,19 @@ int32_t run_window(const WindowCfg& cfg, int32_t num_seqs, const int32_t* seq_le
     {
         buf_elems = static_cast<int64_t>(cfg.max_nodes) * cfg.matrix_seq_dim;
     }
+    const bool tb_mode = cfg.band_mode == static_band_traceback || cfg.band_mode == adaptive_band_traceback;
+    ScoreBuf<ScoreT> sb_tb; // traceback modes: max_pred_dist score rows (allocate_block.hpp:333-334) + the trace matrix
+    std::vector<int8_t> trace8;
+    std::vector<int16_t> trace16;
+    if (tb_mode)
+    {
+        sb_tb.data.assign(static_cast<int64_t>(cfg.max_pred_dist) * cfg.matrix_seq_dim, 0);
+        if (cfg.max_pred_dist > 127)
+            trace16.assign(buf_elems, 0);
+        else
+            trace8.assign(buf_elems, 0);
+        buf_elems = 0;
+    }
     sb.data.assign(buf_elems, 0);
     const float banded_buffer_size = static_cast<float>(cfg.max_nodes) * static_cast<float>(cfg.matrix_seq_dim);
     int32_t scores_width           = 0;
@@ -1170,7 +1499,32 @@ int32_t run_window(const WindowCfg& cfg, int32_t num_seqs, const int32_t* seq_le
         }
         else
         {
-            return generic_error; // traceback band modes are not restated yet
+            // static_band_traceback / adaptive_band_traceback (cudapoa_kernels.cuh:270-346): scores keep max_pred_dist rows,
+            // the trace matrix max_nodes rows; TraceT = int8 unless max_banded_pred_distance > 127 (cudapoa_limits.hpp:56-60)
+            const bool adaptive_tb = cfg.band_mode == adaptive_band_traceback && cfg.band_width < MAX_ADAPTIVE_BW;
+            auto run_tb = [&](int32_t rerun, bool adaptive) {
+                if (cfg.max_pred_dist > 127)
+                    return nw_banded_tb<ScoreT, int16_t>(g, node_count, read, len, sb_tb, trace16, banded_buffer_size, aln_graph.data(),
+                                                          aln_read.data(), cfg.band_width, cfg.max_pred_dist, cfg.gap, cfg.mismatch, cfg.match,
+                                                          rerun, adaptive, cells_out);
+                return nw_banded_tb<ScoreT, int8_t>(g, node_count, read, len, sb_tb, trace8, banded_buffer_size, aln_graph.data(), aln_read.data(),
+                                                     cfg.band_width, cfg.max_pred_dist, cfg.gap, cfg.mismatch, cfg.match, rerun, adaptive, cells_out);
+            };
+            if (adaptive_tb)
+            {
+                alen = run_tb(0, true);
+                if (alen == SHIFT_LEFT || alen == SHIFT_RIGHT)
+                    alen = run_tb(alen, true);
+            }
+            else
+            {
+                alen = run_tb(0, false);
+            }
+            if (alen == NW_TRACEBACK_BUFFER_FAILED)
+            {
+                err = static_cast<uint8_t>(exceeded_maximum_predecessor_distance);
+                break;
+            }
         }
         if (alen == NW_BACKTRACK_FAILED)
         {
@@ -1410,8 +1764,18 @@ int32_t oracle_graph_nw(OracleGraphHandle* h, const uint8_t* read, int32_t read_
         sb.data.assign(static_cast<size_t>(max_nodes) * W, 0);
         return nw_full<int16_t>(g, g.node_count, read, read_length, sb, W, alignment_graph, alignment_read, gap, mismatch, match, nullptr);
     }
-    sb.data.assign(static_cast<size_t>(max_nodes) * matrix_seq_dim, 0);
     float bufsz = static_cast<float>(max_nodes) * static_cast<float>(matrix_seq_dim);
+    if (mode == static_band_traceback || mode == adaptive_band_traceback)
+    {
+        // the harness of Test_CudapoaNW.cu:306-442 (runNWbandedTB): one call, rerun = 0, int16 scores and traces,
+        // score_matrix_height = BatchConfig::max_banded_pred_distance = 2 x band width (batch.cu:46)
+        const int32_t height = 2 * align_up(band_width, MIN_BW);
+        sb.data.assign(static_cast<size_t>(height) * matrix_seq_dim, 0);
+        std::vector<int16_t> trace(static_cast<size_t>(max_nodes) * matrix_seq_dim, 0);
+        return nw_banded_tb<int16_t, int16_t>(g, g.node_count, read, read_length, sb, trace, bufsz, alignment_graph, alignment_read, band_width,
+                                              height, gap, mismatch, match, 0, mode == adaptive_band_traceback, nullptr);
+    }
+    sb.data.assign(static_cast<size_t>(max_nodes) * matrix_seq_dim, 0);
     if (mode == 1)
         return nw_banded<int16_t>(g, g.node_count, read, read_length, sb, bufsz, alignment_graph, alignment_read, band_width, gap, mismatch,
                                   match, 0, false, nullptr);

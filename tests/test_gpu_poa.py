@@ -238,3 +238,42 @@ def test_static_band_512_and_128_vs_reference():
         ours = run_ours(win_nseq, seq_len, data, cfg)
         ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, bw, 1)
         assert_same_consensus(ours, ref, "reference bw=%d" % bw)
+
+
+# ---- traceback band modes (cudapoa_nw_tb_banded.cuh): static / adaptive band with a trace matrix and a score ring ----
+@pytest.mark.parametrize("band_mode,max_pred", [("static_band_traceback", 0), ("adaptive_band_traceback", 0), ("static_band_traceback", 100),
+                                                ("adaptive_band_traceback", 60)])
+def test_traceback_band_modes_vs_oracle_and_reference(band_mode, max_pred, device_fdiv):
+    # max_pred 0 -> BatchConfig default 2 x band (int16 traces); 100 / 60 -> int8 traces and a short score ring
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(40, 700, 12, 14, 7, 7, seed0=77)
+    cfg = cudapoa.make_config(1024, 16, 128, band_mode, max_pred_dist=max_pred)
+    ours = run_ours(win_nseq, seq_len, data, cfg)
+    orc = ol.poa_run(synth.split_windows(win_nseq, seq_len, data), _cfg8(cfg))
+    assert_same_consensus(ours, orc, "oracle")
+    assert ours["cells"] == int(orc["cells"].sum())
+    assert (ours["status"] == 0).sum() >= 30
+    if ref_lib.have_gwref():
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 128, cfg.band_mode, max_pred_dist=max_pred)
+        assert_same_consensus(ours, ref, "reference")
+
+
+def test_traceback_band_mode_msa_and_long_reads_vs_reference(device_fdiv):
+    from genomeworks_b200 import cudapoa, synth
+    # MSA output through the traceback alignment
+    win_nseq, seq_len, data = synth.poa_windows(12, 500, 10, 10, 5, 5, seed0=5)
+    cfg = cudapoa.make_config(1024, 16, 256, "adaptive_band_traceback")
+    ours = run_ours(win_nseq, seq_len, data, cfg, msa=True)
+    if ref_lib.have_gwref():
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, 256, cfg.band_mode, msa=True)
+        assert list(ours["status"]) == list(ref["status"])
+        assert ours["msa"] == ref["msa"]
+    # 6 kb reads: int32 scores, band starts beyond one row stride (the stray boundary write of set_score_tb lands in other ring slots)
+    win_nseq, seq_len, data = synth.poa_windows(6, 6000, 8, 120, 60, 60, seed0=9, max_read_len=6144)
+    cfg = cudapoa.make_config(6144, 8, 256, "static_band_traceback")
+    ours = run_ours(win_nseq, seq_len, data, cfg, mem=16 << 30)
+    orc = ol.poa_run(synth.split_windows(win_nseq, seq_len, data), _cfg8(cfg))
+    assert_same_consensus(ours, orc, "oracle")
+    if ref_lib.have_gwref():
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 6144, 8, 256, cfg.band_mode)
+        assert_same_consensus(ours, ref, "reference")

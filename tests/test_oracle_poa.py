@@ -73,14 +73,15 @@ NODES_STR = "TTTAACCTAATAAATCAGTGAAGATTTAAAATATGATAATTATTGATTTTGGTGAGAGTGCAAAGAA
 READ_STR = "TTTCACCTAGAAAATCAGTGAAGATTTAACAAAAAAAAAAAAAAAAAAAAAAAAATATTGATAATTATTGATTTTGGTGAGAGTGCAAAGCAATTGGCTACCCTCATAAGCTGAGCAGAAGATAAGATAGACAACAGAAGATAGAATAGTTAAACCATGATAGGTACAGACTGCAAAAAAATTCGATAAATATTAAAATTTAGGGCTTTAGTATATATTGATGACTGAGAAAAATCGTGATGTGCAATTGTGCGTGACATGTAGAATTGCCTTAAATAAAATTTAATCTGTCACTGAAGCTATATTTATATTCAGGAAGGATATATCCCAGTCATTGCTTTTCTTAATAAGTGCCCATGTTCCAAGTTTAGCCTAATTAAAAACTTTATGTCTTCTATATCAGAATAGTCATTAATGCACAGAAACAATTTGCGAAGGCATTATGTAGCAAAAACATAAAAAATTATTGCAGCCAAATAATGAATAAAAGTAACACAATCATTTAAAAAAATTATTATGTACTTCTAAAC"
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+# modes 3 / 4 = static / adaptive band with traceback matrix: NWStaticBandTracebackvsFull, NWAdaptiveBandTracebackvsFull (:491-511)
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 def test_nw_banded_equals_full(mode):
     n = len(NODES_STR)
     edges = [[i + 1] for i in range(n - 1)] + [[]]
     g = ol.OGraph(NODES_STR, edges, sorted_graph=list(range(n)))
     rf, agf, arf = g.nw(READ_STR, mode=0)
     # BatchConfig(1024, 2, 128, static/adaptive) -> matrix_sequence_dimension 136 / 272 (Test_CudapoaNW.cu:326-327)
-    msd = 136 if mode == 1 else 272
+    msd = 136 if mode in (1, 3) else 272
     rb, agb, arb = g.nw(READ_STR, mode=mode, band_width=128, max_nodes=3072, matrix_seq_dim=msd)
     assert rf > 0 and rb == rf
     assert agb == agf and arb == arf
@@ -156,7 +157,7 @@ def test_end2end_golden_full_band():
 
 
 # ---- Test_CudapoaBatch.cu:155-203: 3 x 'A'*1023 -> consensus == input --------------------------------
-@pytest.mark.parametrize("band_mode", [0, 1, 2])
+@pytest.mark.parametrize("band_mode", [0, 1, 2, 3, 4])
 def test_identity_consensus(band_mode):
     seq = "A" * 1023
     cfg = ol.batch_config(1024, 10, 256, band_mode)
@@ -167,7 +168,7 @@ def test_identity_consensus(band_mode):
 
 
 # ---- pygenomeworks/test/test_cudapoa_bindings.py::test_cudapoa_complex_batch ------------------------
-@pytest.mark.parametrize("band_mode", [0, 1, 2])
+@pytest.mark.parametrize("band_mode", [0, 1, 2, 3, 4])
 def test_complex_batch_consensus_equals_reference(band_mode):
     random.seed(2)
     read_len = 500

@@ -27,7 +27,10 @@ else:
     cfg = cudapoa.make_config(mseq, 32, 256, "adaptive_band", adaptive_storage_factor=factor)
     mem = int(n * (factor * 32.5e6 + 20e6) * mseq / 10240) + (2 << 30)
     ref_args = (mseq, 32, 256, 2)
-b = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, config=cfg)
+MSA = "--msa" in sys.argv
+if MSA and which != "c2":
+    mem += int(n * 1.2e6 * 32)  # MSA rows + per-read node paths
+b = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, output_type="msa" if MSA else "consensus", config=cfg)
 print("kernel", os.environ.get("GWB200_POA_KERNEL", "v2"), "max_poas", b.max_poas, "resident", b.resident_windows, flush=True)
 for it in range(3):
     b.reset()
@@ -35,7 +38,12 @@ for it in range(3):
     b.enable_timers(it == 2)
     t1 = time.time()
     b.generate_poa()
-    c, cov, lens, st = b.get_consensus_arrays()
+    if MSA:
+        msa, st_list = b.get_msa()
+        st = np.array(st_list)
+        c = cov = lens = None
+    else:
+        c, cov, lens, st = b.get_consensus_arrays()
     t2 = time.time()
     print("ours: generate+get %.1f ms, kernel %.2f ms, cells %.3e, ok=%d  -> %.0f windows/s" % ((t2 - t1) * 1e3, b.last_kernel_ms(), b.last_cells(),
                                                                                              int((st == 0).sum()), n / (b.last_kernel_ms() / 1e3)), flush=True)
@@ -45,6 +53,10 @@ tot = max(1, sum(tm.values()))
 if aux:
     print("row probes (share of dp_rows):", {k: "%.1f%%" % (100.0 * v / max(1, tm["dp_rows"])) for k, v in aux.items()})
 print("phase shares:", {k: "%.1f%%" % (100.0 * v / tot) for k, v in tm.items()}, "cycles/window %.3e" % (tot / n), flush=True)
+if MSA:
+    print("msa: rows of window 0:", len(msa[0]), "columns:", len(msa[0][0]) if msa[0] else 0)
+    b.close()
+    sys.exit(0)
 ours = [bytes(c[i, :lens[i]]).decode() for i in range(n)]
 b.close()
 if "--ref" in sys.argv and ref_lib.have_gwref():
