@@ -461,6 +461,29 @@ int gwb200_poa_decode_error(int32_t status, char* message, int32_t message_len, 
     return 0;
 }
 
+int64_t gwb200_poa_estimate_max_poas(const gwb200_poa_config* cfg, int32_t msa_flag, float gpu_memory_usage_quota, int16_t mismatch_score,
+                                     int16_t gap_score, int16_t match_score)
+{
+    if (!cfg)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "cfg is null");
+    if (int rc = validate_config(*cfg))
+        return rc;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return set_error(GWB200_E_CUDA, "no usable CUDA device: this engine has no CPU fallback");
+    }
+    const int32_t score_bytes = use32bit_score(*cfg, gap_score, mismatch_score, match_score) ? 4 : 2;
+    const int32_t size_bytes  = use32bit_size(*cfg) ? 4 : 2;
+    const bool tb             = cfg->band_mode == GWB200_POA_STATIC_BAND_TRACEBACK || cfg->band_mode == GWB200_POA_ADAPTIVE_BAND_TRACEBACK;
+    const Sizes sz            = compute_sizes(*cfg, score_bytes, size_bytes, msa_flag != 0, tb, cfg->max_banded_pred_distance > INT8_MAX ? 2 : 1);
+    const int64_t per         = sz.dev_per_poa + sz.dev_per_matrix;
+    if (per <= 0)
+        return 0;
+    return static_cast<int64_t>(static_cast<double>(gpu_memory_usage_quota) * static_cast<double>(free_b)) / per;
+}
+
 int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* stream, int64_t max_gpu_mem, int8_t output_mask,
                             const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score, int16_t match_score)
 {

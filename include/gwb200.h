@@ -104,6 +104,12 @@ int gwb200_poa_init(void);
 /* cudapoa::decode_error(), cudapoa.hpp:55 -- writes NUL-terminated strings; unknown status -> GWB200_E_RUNTIME */
 int gwb200_poa_decode_error(int32_t status, char* message, int32_t message_len, char* hint, int32_t hint_len);
 
+/* BatchBlock::estimate_max_poas(batch_size, msa_flag, memory_usage_quota, mismatch, gap, match) -- allocate_block.hpp:403-449:
+ * how many windows of this configuration one batch holds when it may use `gpu_memory_usage_quota` of the currently free memory
+ * of the current device (this engine's own arena layout). Used by get_multi_batch_sizes (utils.hpp:55-68). < 0 on error. */
+int64_t gwb200_poa_estimate_max_poas(const gwb200_poa_config* cfg, int32_t msa_flag, float gpu_memory_usage_quota, int16_t mismatch_score,
+                                     int16_t gap_score, int16_t match_score);
+
 typedef struct gwb200_poa_batch gwb200_poa_batch; /* opaque: one cudapoa::Batch */
 
 /* create_batch(device_id, stream, max_gpu_mem, output_mask, batch_size, gap_score, mismatch_score, match_score)
