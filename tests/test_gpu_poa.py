@@ -20,24 +20,6 @@ def _cfg8(cfg):
                      cfg.alignment_band_width, cfg.max_sequences_per_poa, cfg.band_mode, cfg.max_banded_pred_distance], dtype=np.int32)
 
 
-@pytest.fixture(scope="module")
-def device_fdiv():
-    """Installs the device's __fdividef as the oracle's division (cudapoa_nw_banded.cuh:207 under -use_fast_math)."""
-    from genomeworks_b200 import cudapoa
-    cache = {}
-
-    def fdiv(a, b):
-        k = (a, b)
-        if k not in cache:
-            cache[k] = float(cudapoa.device_fdividef([a], [b])[0])
-        return cache[k]
-
-    cb = ol.FDIV_T(fdiv)
-    ol.lib().oracle_set_fdiv(C.cast(cb, C.c_void_p))
-    yield cb
-    ol.lib().oracle_set_fdiv(None)
-
-
 def run_ours(win_nseq, seq_len, data, cfg, msa=False, mem=8 << 30, weights=None, gap=-8, mismatch=-6, match=8):
     from genomeworks_b200 import cudapoa
     batch = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, output_type="msa" if msa else "consensus", config=cfg,
