@@ -1,5 +1,5 @@
 """Development aid: time a POA config (ours, optional v1 A/B via GWB200_POA_KERNEL=v1) and print per-phase cycle shares.
-usage: quick_poa.py {c2|c3} [n_windows] [--ref] [--factor F]   (env GWB200_POA_WARPS / GWB200_POA_POOL_KB: kernel experiments)"""
+usage: quick_poa.py {c2|c3} [n_windows] [--ref] [--factor F] [--len L] [--msa] [--band-mode NAME (c2 only)]   (env GWB200_POA_WARPS / GWB200_POA_POOL_KB: kernel experiments)"""
 import os
 import sys
 import time
@@ -15,9 +15,10 @@ which = sys.argv[1] if len(sys.argv) > 1 else "c2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else (1024 if which == "c2" else 148)
 if which == "c2":
     win_nseq, seq_len, data = synth.poa_windows(n, 1000, 16, 20, 10, 10, seed0=1000, max_read_len=1024)
-    cfg = cudapoa.make_config(1024, 16, 256, "static_band")
+    bm = sys.argv[sys.argv.index("--band-mode") + 1] if "--band-mode" in sys.argv else "static_band"  # e.g. static_band_traceback
+    cfg = cudapoa.make_config(1024, 16, 256, bm)
     mem = 16 << 30
-    ref_args = (1024, 16, 256, 1)
+    ref_args = (1024, 16, 256, cfg.band_mode)
     factor = 2.0
 else:
     factor = float(sys.argv[sys.argv.index("--factor") + 1]) if "--factor" in sys.argv else 6.0
