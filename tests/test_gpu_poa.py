@@ -259,3 +259,23 @@ def test_traceback_band_mode_msa_and_long_reads_vs_reference(device_fdiv):
     if ref_lib.have_gwref():
         ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 6144, 8, 256, cfg.band_mode)
         assert_same_consensus(ours, ref, "reference")
+
+
+def test_c3_shape_storage_factor_status_parity_vs_reference():
+    """10 kb x 32-read windows with the default adaptive_storage_factor 2.0 fail with
+    exceeded_adaptive_banded_matrix_size in the reference; the status must be the same here, and at factor 3.0 (bench.py's C3
+    configuration) every window succeeds with identical consensus and coverage."""
+    if not ref_lib.have_gwref():
+        pytest.skip("reference library not built")
+    from genomeworks_b200 import cudapoa, synth
+    win_nseq, seq_len, data = synth.poa_windows(4, 10000, 32, 200, 100, 100, seed0=1000, max_read_len=10240)
+    for factor in (2.0, 3.0):
+        cfg = cudapoa.make_config(10240, 32, 256, "adaptive_band", adaptive_storage_factor=factor)
+        ours = run_ours(win_nseq, seq_len, data, cfg, mem=4 << 30)
+        ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 10240, 32, 256, 2, adaptive_storage_factor=factor, mem_fraction=0.05,
+                                  max_windows_per_batch=4)
+        assert_same_consensus(ours, ref, "reference, factor %g" % factor)
+        if factor == 2.0:
+            assert set(ours["status"]) == {cudapoa.exceeded_adaptive_banded_matrix_size}
+        else:
+            assert (ours["status"] == 0).all()
