@@ -210,12 +210,13 @@ def test_int32_sizes_long_window_vs_reference():
 
 
 def test_static_band_512_and_128_vs_reference():
-    """Other kernel configurations: 1 chunk (band 128, one warp) and 4 chunks (band 512, four warps x one chunk)."""
+    """Other kernel configurations: 1 chunk (band 128, one warp), 3 chunks (band 384: three of four warps take part in the rows)
+    and 4 chunks (band 512, four warps x one chunk)."""
     if not ref_lib.have_gwref():
         pytest.skip("oracle/_ref/libgwref.so not built")
     from genomeworks_b200 import cudapoa, synth
     win_nseq, seq_len, data = synth.poa_windows(40, 900, 10, 20, 12, 12, seed0=555, max_read_len=1024)
-    for bw in (128, 512):
+    for bw in (128, 384, 512):
         cfg = cudapoa.make_config(1024, 16, bw, "static_band")
         ours = run_ours(win_nseq, seq_len, data, cfg)
         ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 1024, 16, bw, 1)
