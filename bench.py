@@ -194,7 +194,6 @@ def main():
     ap.add_argument("--windows", type=int, default=0, help="windows (or pairs) per GPU per step")
     ap.add_argument("--factor", type=float, default=0.0, help="override adaptive_storage_factor of the workload (C3 default 3.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gpu-reference", action="store_true", help="also time the reference CUDA kernels (oracle/_ref) on rank 0")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -375,22 +374,6 @@ def main():
                                             "sample": "oracle/_ref/libspoa_ref.so not built"}
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
-        if args.gpu_reference:
-            try:
-                import ref_lib
-                if ref_lib.have_gwref():
-                    batch.close()
-                    bm = {"full_band": 0, "static_band": 1, "adaptive_band": 2}[wp["band_mode"]]
-                    rr = ref_lib.ref_poa_run(win_nseq, seq_len, data, wp["max_seq"], wp["reads"], wp["band"], bm,
-                                             adaptive_storage_factor=wp["factor"], mem_fraction=0.9, max_windows_per_batch=n_win)
-                    rr = ref_lib.ref_poa_run(win_nseq, seq_len, data, wp["max_seq"], wp["reads"], wp["band"], bm,
-                                             adaptive_storage_factor=wp["factor"], mem_fraction=0.9, max_windows_per_batch=n_win)
-                    same = all(bytes(c[i, :lens[i]]).decode() == rr["consensus"][i] for i in range(n_win)) and list(rr["status"]) == list(st)
-                    line["gpu_reference"] = {"value": n_win / (rr["timings"][1] / 1e3), "unit": "windows/s",
-                                             "what": "unmodified reference cudapoa rebuilt for sm_100a, generate_poa+get_consensus wall time, "
-                                                     "same windows, same GPU", "batches": int(rr["timings"][2]), "identical_outputs": bool(same)}
-            except Exception as e:  # pragma: no cover
-                line["gpu_reference"] = {"value": None, "what": "failed: %r" % (e,)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

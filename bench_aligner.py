@@ -72,20 +72,6 @@ def run_aligner_bench(args, wp, rank, world, local_rank, barrier, max_over_ranks
                     "d2h_bytes_per_step": int(sum(len(r.actions) for r in res)) * 5 + 8 * n},
             "gpu_launches": int(timed_launches), "gpu_launches_total": int(L.gwb200_kernel_launch_count() - launches0), "clocks": clocks,
             "cpu_baseline": {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference",
-                             "sample": "no CPU implementation of this path is named by the reference (SURVEY.md 8d); see gpu_reference"},
+                             "sample": "no CPU implementation of this path is named by the reference (SURVEY.md 8d); the reference's GPU kernel is compared by tests/tools/gpu_reference.py"},
         }
-        if args.gpu_reference:
-            try:
-                import ref_lib
-                if ref_lib.have_gwref():
-                    al.close()
-                    ref_lib.ref_aligner_run(ql, qd, tl, td, wp["max_bw"], max_device_memory=32 << 30)
-                    rr = ref_lib.ref_aligner_run(ql, qd, tl, td, wp["max_bw"], max_device_memory=32 << 30)
-                    same = all((r.convert_to_cigar(True) == rr["cigar_extended"][i]) and (int(r.is_optimal) == rr["is_optimal"][i])
-                               for i, r in enumerate(res))
-                    line["gpu_reference"] = {"value": n / (rr["timings"][1] / 1e3), "unit": "pairs/s",
-                                             "what": "unmodified reference AlignerGlobalMyersBanded rebuilt for sm_100a, align_all+sync wall time",
-                                             "identical_outputs": bool(same)}
-            except Exception as e:  # pragma: no cover
-                line["gpu_reference"] = {"value": None, "what": "failed: %r" % (e,)}
         print(json.dumps(line))

@@ -231,19 +231,3 @@ class CudaAlignerBatch:
 
     def reset(self):
         self._aligner.reset()
-
-
-def smoke_check():
-    """Used by __graft_entry__.smoke(): one alignment on the device against the CPU oracle."""
-    import oracle_lib as ol
-    q = "ACGTTGCATGCATGGCATTACGATCGATCGATTTAGCAGCTAGCTAGTCGATGCTAGCTAGCTAGTCGATCGAT" * 6
-    t = q[:100] + "TT" + q[100:250] + q[260:]
-    al = FixedBandAligner(64)
-    assert al.add_alignment(q, t) == success
-    al.align_all()
-    al.sync_alignments()
-    r = al.get_alignments()[0]
-    o = ol.myers_align(q, t, 64)
-    assert r.status == o["status"] and int(r.is_optimal) == o["is_optimal"] and r.convert_to_cigar() == o["cigar"], (r.convert_to_cigar(), o["cigar"])
-    print("smoke: banded Myers CIGAR matches the oracle:", r.convert_to_cigar()[:60])
-    al.close()
