@@ -210,3 +210,25 @@ def test_msa_rows_strip_to_inputs():
     assert len(set(len(r) for r in rows)) == 1
     for row, rd in zip(rows, reads):
         assert row.replace("-", "") == rd
+
+
+# ---- outputs of the unmodified reference kernels (tests/golden/make_reference_fixture.py, run on a B200) ---------------
+@pytest.mark.parametrize("case_idx", range(5))
+def test_oracle_matches_reference_kernel_fixture(case_idx):
+    """Pins the CPU restatement to the reference ITSELF: consensus, coverage and status that libgwref.so (the reference's
+    own kernels rebuilt for sm_100a) produced for 12 synthetic windows in every band mode, incl. both traceback modes."""
+    import gzip
+    import json
+    from genomeworks_b200 import synth
+    fx = json.load(gzip.open(os.path.join(GOLDEN, "reference_kernel_outputs.json.gz"), "rt"))
+    gen = fx["generator"]
+    win_nseq, seq_len, data = synth.poa_windows(gen["n_windows"], gen["backbone"], gen["reads"], gen["mut"], gen["ins"], gen["dele"],
+                                                seed0=gen["seed0"])
+    case = fx["cases"][case_idx]
+    assert case["oracle_with_ieee_division_identical"]  # recorded at generation time: div.approx vs IEEE does not matter for these windows
+    cfg = ol.batch_config(fx["max_sequence_size"], fx["max_sequences_per_poa"], case["band_width"], case["band_mode"],
+                          max_pred_dist=case["max_pred"])
+    res = ol.poa_run(synth.split_windows(win_nseq, seq_len, data), cfg)
+    assert [int(x) for x in res["status"]] == case["status"]
+    assert list(res["consensus"]) == case["consensus"]
+    assert [[int(v) for v in cv] for cv in res["coverage"]] == case["coverage"]
