@@ -2,18 +2,24 @@
 // consensus / coverage / MSA / status to the reference kernels), restructured around what the v1 profile showed
 // (profiles/r01_poa_v1_*.md: every phase stalled on dependent global loads, issue slots 15-22 % busy):
 //
-//   DP rows      per-row graph metadata (node, base, predecessor rows, sink flag) is fetched 32 rows at a time by the
-//                lanes, one group ahead of its use, and broadcast by shuffle; the last R score rows live in a shared
-//                memory ring so the predecessor row is read from shared memory, not L2/HBM; each row is still written
-//                to HBM exactly once with aligned vector stores (the algorithmic sizeof(ScoreT) bytes per cell).
+//   DP rows      the CTA has up to 4 warps, band chunk c (128 columns, 4 cells per lane) belongs to warp c % NW and only
+//                min(NW, chunks) warps take part in an alignment's rows (named barrier); per-row graph metadata (node, base,
+//                predecessor rows and band starts, ring distances, sink flag) is fetched 32 rows at a time by the lanes, one
+//                group ahead of its use, packed into three words and broadcast by three shuffles; the last R score rows live
+//                in a shared-memory ring so predecessor rows are read from shared memory, not L2/HBM; chunk carries are
+//                exchanged through shared memory and folded by one redux.sync.max per chunk; each row is written to HBM
+//                exactly once with aligned vector stores (the algorithmic sizeof(ScoreT) bytes per cell).
 //   end cell     lane-parallel over the sink rows.
 //   traceback    warp-uniform walk over a shared-memory tile (32 rows x 64 columns of scores + the rows' metadata)
 //                that the warp refills with coalesced loads; the reference's per-step preference order
-//                (cudapoa_nw_banded.cuh:440-534) and adaptive-band abort tests are evaluated unchanged on tile values.
+//                (cudapoa_nw_banded.cuh:440-534) and adaptive-band abort tests are evaluated unchanged on tile values;
+//                runs of "diagonal through the first predecessor" are taken 32 steps at a time (pointer doubling over the
+//                tile's first-predecessor links, lane k verifies step k).
 //   add alignment lane-parallel over read bases (new-node ids by ballot prefix sum); conflict-free because a path
 //                visits every node, ring and edge at most once.
-//   topsort      same Kahn FIFO order (cudapoa_topsort.cuh:45-97), in-degree counters and the queue window in shared
-//                memory, children's adjacency fetched when they are enqueued.
+//   topsort      same Kahn FIFO order (cudapoa_topsort.cuh:45-97): in-degree counters, a tagged window of the FIFO and as
+//                many "only child" words as fit live in shared memory; single-child chains are followed in a register.
+//   traceback band modes: poa_kernels_tb.cuh (one-warp routine hosted by the NW = 1 instantiation).
 #pragma once
 #include <type_traits>
 
@@ -33,7 +39,7 @@ constexpr int32_t kTileCols = 64;
 
 struct V2Extra
 {
-    int4* row_meta;     // [n_windows][max_nodes + 1] : {node, pred0 row, pred1 row, base | pc << 8 | sink << 16}
+    int4* row_meta;     // [n_windows][max_nodes + 1] : {node, pred0 row, pred1 row, base | pc << 8 | sink << 16 | band_start / 4 << 17}
     void* rd_node;      // SizeT [n_windows][max_seq_aligned] : graph node aligned to each read base (-1 = insertion)
     int32_t rd_capacity;
     int32_t pool_bytes; // dynamic shared memory per CTA
