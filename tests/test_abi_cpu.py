@@ -103,3 +103,19 @@ def test_cpp_api_headers_compile_and_link():
            "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "genomeworks_b200"), "-Wl,-rpath,/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     assert os.path.exists(out)
+
+
+@pytest.mark.parametrize("src", ["tests/cpp/test_cpp_api.cpp", "tests/cpp/test_utils_cpu.cpp", "tools/cudapoa_cli.cpp"])
+def test_cpp_headers_are_cxx14_clean(src):
+    """The reference builds its callers with -std=c++14 (cmake/CXX.cmake): the drop-in headers must compile there, warning-free."""
+    cmd = ["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(ROOT, src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_c_header_is_plain_c():
+    """include/gwb200.h is the FFI boundary: it must compile as C (no C++ or torch types in the signatures)."""
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "gwb200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
