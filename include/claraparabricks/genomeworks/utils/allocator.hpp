@@ -5,6 +5,8 @@
 // arenas, so the allocator here carries exactly that budget.
 #pragma once
 
+#include "cudautils.hpp" // CudaStream, make_cuda_stream, GW_CU_CHECK_ERR come along with the allocator in the reference too
+
 #include <cstdint>
 #include <cuda_runtime_api.h>
 
