@@ -119,3 +119,14 @@ def test_c_header_is_plain_c():
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "gwb200.h")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_pygenomeworks_import_alias():
+    """`import genomeworks.cudapoa` style imports of pygenomeworks callers resolve to this engine through genomeworks_b200/compat."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from genomeworks.cudapoa import CudaPoaBatch, status_to_str; from genomeworks.cudaaligner import CudaAlignerBatch;"
+            "import genomeworks.cuda as cuda; assert cuda.CudaStream and cuda.CudaRuntimeError and cuda.cuda_get_mem_info;"
+            "assert cuda.cuda_get_device_count() >= 0; import genomeworks_b200.cudapoa as m; assert CudaPoaBatch is m.CudaPoaBatch;"
+            "print('ok')") % (ROOT, os.path.join(ROOT, "genomeworks_b200", "compat"))
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
