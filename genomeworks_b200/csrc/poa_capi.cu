@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "poa_kernels.cuh"
 #include "poa_kernels_v2.cuh"
+#include "poa_kernels_v3.cuh"
 
 #include <cstdlib>
 
@@ -100,7 +101,11 @@ struct gwb200_poa_batch
     uint8_t* d_block = nullptr;
     DeviceParams P{};
     V2Extra X{};
+    V3Extra Y{};
     bool use_v2 = true;
+    bool use_v3 = true;      // third-generation kernel (one warp per window, persistent grid); v2/v1 remain for the traceback band
+                             // modes, bands wider than 1536 and reads of 64 k bases and more
+    int32_t v3_ctas_per_sm = 0;
     bool tb_mode = false;    // static_band_traceback / adaptive_band_traceback
     int32_t trace_bytes = 2; // sizeof(TraceT): 1 unless max_banded_pred_distance > 127 (cudapoa_limits.hpp:56-60)
     int32_t nw_override = 0;
@@ -207,6 +212,59 @@ V2Choice choose_v2(const gwb200_poa_batch* b)
 // 4-warp kernels, measured best of 5..8 on C3), 24 KB (16-bit scores), 12 KB (one-warp kernels with 16-bit scores, 16 per SM).
 // Reads longer than ~10 kb get a pool that holds the staged read plus two rows of the widest band (fewer resident windows,
 // which HBM capacity limits anyway at that size).
+// Dynamic shared memory per CTA of the v3 kernel. The resident windows of one SM share its 227 KB: the pool is what one CTA gets
+// when the batch's capacity (HBM) is spread over the SMs, at most 16 CTAs per SM (registers) -- a batch that HBM limits to a
+// few windows per SM gives each of them a deeper ring of score rows. Never less than two traceback tile buffers or two rows
+// of the widest band.
+int32_t v3_pool_bytes(gwb200_poa_batch* b)
+{
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device_id);
+    int smem_sm = 233472;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, b->device_id);
+    int32_t ctas = static_cast<int32_t>(std::min<int64_t>(16, std::max<int64_t>(1, (static_cast<int64_t>(b->max_poas) + sms - 1) / sms)));
+    if (const char* c = std::getenv("GWB200_POA_CTAS_PER_SM")) // development switch
+        ctas = std::max(1, std::min(32, std::atoi(c)));
+    if (const char* kb = std::getenv("GWB200_POA_POOL_KB")) // development switch
+    {
+        b->v3_ctas_per_sm = ctas;
+        return std::atoi(kb) * 1024;
+    }
+    const int64_t max_bw  = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
+    const int64_t need    = std::max<int64_t>(2 * (max_bw + 8) * b->score_bytes, 2 * (b->score32 ? TileBuf<int32_t>::kBytes : TileBuf<int16_t>::kBytes));
+    const int64_t statics = sizeof(V3Shared) + 64;
+    int64_t pool          = smem_sm / ctas - 1024 - statics;
+    pool                  = std::min<int64_t>(pool, 96 * 1024) / 256 * 256;
+    pool                  = std::max<int64_t>(pool, align_up64(need, 256));
+    b->v3_ctas_per_sm     = ctas;
+    return static_cast<int32_t>(pool);
+}
+
+template <typename ScoreT, typename SizeT>
+int32_t v3_action(gwb200_poa_batch* b, int action)
+{
+    const bool bulk    = b->Y.use_bulk != 0;
+    auto kfn           = bulk ? poa_window_kernel_v3<ScoreT, SizeT, true> : poa_window_kernel_v3<ScoreT, SizeT, false>;
+    const int32_t smem = b->X.pool_bytes;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, 32, smem) != cudaSuccess)
+    {
+        cudaGetLastError();
+        nb = 0;
+    }
+    if (action == 1)
+        return nb;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device_id);
+    const int32_t grid = std::max(1, std::min(b->poa_count, std::max(1, nb) * sms));
+    cudaMemsetAsync(b->Y.work_counter, 0, sizeof(int32_t), b->stream);
+    kfn<<<grid, 32, smem, b->stream>>>(b->P, b->X, b->Y);
+    return 0;
+}
+
 int32_t v2_pool_bytes(const gwb200_poa_batch* b)
 {
     const int64_t max_bw = (b->cfg.band_mode == GWB200_POA_ADAPTIVE_BAND) ? kMaxAdaptiveBW : b->cfg.alignment_band_width;
@@ -247,6 +305,19 @@ int32_t v2_action(gwb200_poa_batch* b, int action)
 template <typename ScoreT, typename SizeT>
 int32_t typed_action(gwb200_poa_batch* b, int action)
 {
+    if (b->use_v3)
+    {
+        if (action == 0)
+        {
+            b->X.timers = b->timers_on ? b->d_timers : nullptr;
+            if (b->timers_on)
+                cudaMemsetAsync(b->d_timers, 0, sizeof(unsigned long long) * 8 * b->poa_count, b->stream);
+        }
+        const int32_t r = v3_action<ScoreT, SizeT>(b, action);
+        if (action == 0)
+            count_launch();
+        return r;
+    }
     if (b->use_v2)
     {
         if (action == 0)
@@ -637,6 +708,7 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
         b->X.rd_capacity = align_up(std::max(cfg->max_sequence_size, 1), 4) + 8;
         b->X.rd_node     = dc.take<uint8_t>(n * static_cast<int64_t>(b->X.rd_capacity) * S);
         b->d_timers      = dc.take<unsigned long long>(n * 8);
+        b->Y.work_counter = dc.take<int32_t>(64);
         b->X.timers      = nullptr;
         b->X.pool_bytes  = v2_pool_bytes(b);
         b->X.tb_scores   = nullptr;
@@ -671,14 +743,26 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     cudaEventCreate(&b->ev0);
     cudaEventCreate(&b->ev1);
     {
-        const char* k = std::getenv("GWB200_POA_KERNEL"); // development A/B switch: "v1" selects the first-generation kernel
+        const char* k = std::getenv("GWB200_POA_KERNEL"); // development A/B switch: "v1" / "v2" select the earlier kernel generations
         b->use_v2     = !(k && std::string(k) == "v1");
+        b->use_v3     = !(k && (std::string(k) == "v1" || std::string(k) == "v2"));
         {
             // the v2 kernel packs band starts in 15 bits (x4) and needs its staged read plus a few score rows in shared memory
             if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || b->X.pool_bytes > 200 * 1024)
                 b->use_v2 = false; // first-generation kernel
             if (b->tb_mode)
                 b->use_v2 = true; // only the v2 kernel family hosts the traceback-matrix alignment
+            // the v3 kernel packs band starts in 16 bits and serves every score-matrix mode; the traceback-matrix modes stay on v2
+            if (b->cfg.alignment_band_width > kMaxAdaptiveBW || b->cfg.max_sequence_size >= 65536 || b->tb_mode)
+                b->use_v3 = false;
+        }
+        if (b->use_v3)
+        {
+            b->X.pool_bytes = v3_pool_bytes(b);
+            const char* e   = std::getenv("GWB200_POA_BULK"); // development A/B switches
+            b->Y.use_bulk   = (e && std::atoi(e) == 0) ? 0 : 1;
+            e               = std::getenv("GWB200_POA_TB_TMA");
+            b->Y.tb_tma     = (e && std::atoi(e) == 0) ? 0 : 1;
         }
     }
     gwb200_poa_batch_reset(b);

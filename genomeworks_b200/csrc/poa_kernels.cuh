@@ -38,6 +38,7 @@ enum Status : int32_t
     st_exceeded_maximum_predecessor_distance  = 7,
     st_loop_count_exceeded_upper_bound        = 8,
     st_exceeded_maximum_sequence_size         = 2,
+    st_empty_poa_group                        = 11,
     st_generic_error                          = 12
 };
 
@@ -1202,6 +1203,20 @@ __global__ void __launch_bounds__(32, 16) poa_window_kernel(const DeviceParams P
     uint8_t* consensus = P.consensus + static_cast<int64_t>(w) * P.max_consensus;
     uint16_t* coverage = P.coverage + static_cast<int64_t>(w) * P.max_consensus;
 
+    // a group whose reads were all rejected stays in the batch with no read (add_poa_group returns empty_poa_group,
+    // cudapoa_batch.cuh:139-148): nothing to align, and seq_lengths[0] would belong to another window
+    if (wi.num_seqs <= 0)
+    {
+        if (threadIdx.x == 0)
+        {
+            consensus[0]       = 0;
+            P.status[w]        = st_empty_poa_group;
+            P.consensus_len[w] = 0;
+            P.node_count[w]    = 0;
+            P.cells[w]         = 0;
+        }
+        return;
+    }
     // backbone from read 0, cudapoa_kernels.cuh:200-238 (lane-parallel here)
     int32_t node_count = seq_lengths[0];
     for (int32_t n = lane; n < node_count; n += 32)

@@ -1186,6 +1186,20 @@ __global__ void __launch_bounds__(32 * NW, (NW == 4 ? GWB200_POA_NW4_BLOCKS : (N
     uint8_t* consensus = P.consensus + static_cast<int64_t>(w) * P.max_consensus;
     uint16_t* coverage = P.coverage + static_cast<int64_t>(w) * P.max_consensus;
 
+    // a group whose reads were all rejected stays in the batch with no read (add_poa_group returns empty_poa_group,
+    // cudapoa_batch.cuh:139-148): nothing to align, and seq_lengths[0] would belong to another window
+    if (wi.num_seqs <= 0)
+    {
+        if (threadIdx.x == 0)
+        {
+            consensus[0]       = 0;
+            P.status[w]        = st_empty_poa_group;
+            P.consensus_len[w] = 0;
+            P.node_count[w]    = 0;
+            P.cells[w]         = 0;
+        }
+        return;
+    }
     // backbone from read 0 (cudapoa_kernels.cuh:200-238), thread-parallel
     int32_t node_count = seq_lengths[0];
     for (int32_t n = threadIdx.x; n < node_count; n += 32 * NW)

@@ -27,12 +27,14 @@ else:
     win_nseq, seq_len, data = synth.poa_windows(n, L, 32, L // 50, L // 100, L // 100, seed0=1000, max_read_len=mseq)
     cfg = cudapoa.make_config(mseq, 32, 256, "adaptive_band", adaptive_storage_factor=factor)
     mem = int(n * (factor * 32.5e6 + 20e6) * mseq / 10240) + (2 << 30)
+    if "--allmem" in sys.argv:
+        mem = -1
     ref_args = (mseq, 32, 256, 2)
 MSA = "--msa" in sys.argv
 if MSA and which != "c2":
     mem += int(n * 1.2e6 * 32)  # MSA rows + per-read node paths
 b = cudapoa.CudaPoaBatch(cfg.max_sequences_per_poa, cfg.max_sequence_size, mem, output_type="msa" if MSA else "consensus", config=cfg)
-print("kernel", os.environ.get("GWB200_POA_KERNEL", "v2"), "max_poas", b.max_poas, "resident", b.resident_windows, flush=True)
+print("kernel", os.environ.get("GWB200_POA_KERNEL", "v3"), "max_poas", b.max_poas, "resident", b.resident_windows, flush=True)
 for it in range(3):
     b.reset()
     b.add_poa_groups_flat(win_nseq, seq_len, data)
@@ -59,6 +61,8 @@ if MSA:
     b.close()
     sys.exit(0)
 ours = [bytes(c[i, :lens[i]]).decode() for i in range(n)]
+import hashlib
+print("digest", hashlib.sha1(("|".join(ours) + str(list(st))).encode()).hexdigest()[:16], "cov", hashlib.sha1(cov.tobytes()).hexdigest()[:12], flush=True)
 b.close()
 if "--ref" in sys.argv and ref_lib.have_gwref():
     r = ref_lib.ref_poa_run(win_nseq, seq_len, data, *ref_args, adaptive_storage_factor=factor, mem_fraction=0.5, max_windows_per_batch=n)
