@@ -30,35 +30,56 @@ int64_t matrix_size_for_alignment(int32_t query_size, int32_t target_size, int32
     return n_words_band * (static_cast<int64_t>(target_size) + 1);
 }
 
+// Where device buffers come from: cudaMalloc / cudaFree, or the caller's allocator (create_aligner overloads that take a
+// DefaultDeviceAllocator: every buffer is a block of the caller's pool, aligner.cpp:76-124)
+struct MemHooks
+{
+    gwb200_device_alloc_fn alloc = nullptr;
+    gwb200_device_free_fn release = nullptr;
+    void* user                    = nullptr;
+};
+
 template <typename T>
 struct DevBuf
 {
     T* p       = nullptr;
     int64_t n  = 0;
+    const MemHooks* hooks = nullptr;
+    void drop()
+    {
+        if (p)
+        {
+            if (hooks && hooks->release)
+                hooks->release(hooks->user, p, n * static_cast<int64_t>(sizeof(T)));
+            else
+                cudaFree(p);
+        }
+        p = nullptr;
+        n = 0;
+    }
     bool ensure(int64_t count)
     {
         if (count <= n)
             return true;
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        n = 0;
-        int64_t want = count + count / 8 + 64;
-        if (cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)) != cudaSuccess)
+        drop();
+        // exactly what memory_requirement() accounts for (plus 64 elements): a batch admitted at add time fits at align time
+        const int64_t want = count + 64;
+        if (hooks && hooks->alloc)
+        {
+            p = static_cast<T*>(hooks->alloc(hooks->user, want * static_cast<int64_t>(sizeof(T))));
+            if (!p)
+                return false;
+        }
+        else if (cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T)) != cudaSuccess)
         {
             cudaGetLastError();
+            p = nullptr;
             return false;
         }
         n = want;
         return true;
     }
-    void release()
-    {
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
+    void release() { drop(); }
 };
 
 template <typename T>
@@ -113,6 +134,7 @@ struct gwb200_aligner
     int32_t max_bandwidth = 0;
     int64_t max_device_memory = 0;
     int32_t n_sms = 0;
+    MemHooks hooks;
 
     // host inputs
     PinBuf<char> seq_h;
@@ -183,6 +205,12 @@ int gwb200_aligner_reset_max_bandwidth(gwb200_aligner* a, int32_t max_bandwidth)
 
 int gwb200_aligner_create(gwb200_aligner** out, int32_t max_bandwidth, void* stream, int32_t device_id, int64_t max_device_memory)
 {
+    return gwb200_aligner_create_with_allocator(out, max_bandwidth, stream, device_id, max_device_memory, nullptr, nullptr, nullptr);
+}
+
+int gwb200_aligner_create_with_allocator(gwb200_aligner** out, int32_t max_bandwidth, void* stream, int32_t device_id, int64_t max_device_memory,
+                                         gwb200_device_alloc_fn alloc_fn, gwb200_device_free_fn free_fn, void* user)
+{
     if (!out)
         return set_error(GWB200_E_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
@@ -209,6 +237,14 @@ int gwb200_aligner_create(gwb200_aligner** out, int32_t max_bandwidth, void* str
     a->max_device_memory = max_device_memory < 0 ? static_cast<int64_t>(free_b * 0.95) : max_device_memory;
     cudaEventCreate(&a->ev0);
     cudaEventCreate(&a->ev1);
+    if (alloc_fn && free_fn)
+    {
+        a->hooks = MemHooks{alloc_fn, free_fn, user};
+        const MemHooks* h = &a->hooks;
+        a->seq_d.hooks = a->seq_starts_d.hooks = a->max_bw_d.hooks = a->sched_d.hooks = a->counter_d.hooks = a->path_len_d.hooks = h;
+        a->offsets_d.hooks = a->slot_runs_d.hooks = a->runs_d.hooks = a->metadata_d.hooks = a->slot_actions_d.hooks = a->actions_d.hooks = h;
+        a->pv_d.hooks = a->mv_d.hooks = a->qpat_d.hooks = a->score_d.hooks = a->cells_d.hooks = h;
+    }
     *out = a;
     return 0;
 }
@@ -299,6 +335,7 @@ int gwb200_aligner_add_alignment(gwb200_aligner* a, int32_t max_bandwidth, const
 }
 
 int32_t gwb200_aligner_num_alignments(const gwb200_aligner* a) { return a ? a->num_alignments() : 0; }
+int32_t gwb200_aligner_num_results(const gwb200_aligner* a) { return a ? static_cast<int32_t>(a->results.size()) : 0; }
 
 // aligner_global_myers_banded.cpp:260-374
 int gwb200_aligner_align_all(gwb200_aligner* a)
@@ -381,13 +418,14 @@ int gwb200_aligner_sync_alignments(gwb200_aligner* a)
         return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
     DeviceGuard guard(a->device_id);
     const int32_t n = a->num_alignments();
-    a->results.clear();
-    a->results.resize(n);
     if (n == 0 || !a->aligned)
     {
+        // nothing was aligned since the last sync: the previous results stay (the reference keeps its alignments)
         GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream));
         return GWB200_ALN_SUCCESS;
     }
+    a->results.clear();
+    a->results.resize(n);
     GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream)); // offsets + metadata are on the host now
     const int64_t total = a->offsets_h.p[n];
     a->total_len        = total;

@@ -99,6 +99,7 @@ struct gwb200_poa_batch
 
     // device
     uint8_t* d_block = nullptr;
+    bool owns_dblock = true; // false: the block belongs to the caller's allocator (create_batch overload with an allocator)
     DeviceParams P{};
     V2Extra X{};
     V3Extra Y{};
@@ -555,8 +556,29 @@ int64_t gwb200_poa_estimate_max_poas(const gwb200_poa_config* cfg, int32_t msa_f
     return static_cast<int64_t>(static_cast<double>(gpu_memory_usage_quota) * static_cast<double>(free_b)) / per;
 }
 
+static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void* stream, int64_t max_gpu_mem, int8_t output_mask,
+                                 const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score, int16_t match_score, void* ext_block,
+                                 int64_t ext_bytes);
+
 int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* stream, int64_t max_gpu_mem, int8_t output_mask,
                             const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score, int16_t match_score)
+{
+    return poa_batch_create_impl(out, device_id, stream, max_gpu_mem, output_mask, cfg, gap_score, mismatch_score, match_score, nullptr, 0);
+}
+
+int gwb200_poa_batch_create_in_block(gwb200_poa_batch** out, int32_t device_id, void* stream, void* device_block, int64_t device_block_bytes,
+                                     int8_t output_mask, const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score,
+                                     int16_t match_score)
+{
+    if (!device_block || device_block_bytes <= 0 || (reinterpret_cast<uintptr_t>(device_block) & 255) != 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "device_block has to be a 256-byte aligned device allocation");
+    return poa_batch_create_impl(out, device_id, stream, device_block_bytes, output_mask, cfg, gap_score, mismatch_score, match_score, device_block,
+                                 device_block_bytes);
+}
+
+static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void* stream, int64_t max_gpu_mem, int8_t output_mask,
+                                 const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score, int16_t match_score, void* ext_block,
+                                 int64_t ext_bytes)
 {
     if (!out || !cfg)
         return set_error(GWB200_E_INVALID_ARGUMENT, "null argument");
@@ -610,6 +632,9 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     int64_t avail = static_cast<int64_t>(static_cast<double>(free_b) * 0.95);
     if (max_gpu_mem >= 0)
         avail = std::min(avail, max_gpu_mem);
+    const int64_t fixed_dev = 4096 * 2 + 256 * 64; // per-batch constant part of the device block
+    if (ext_block)
+        avail = ext_bytes - fixed_dev; // the caller's block is the budget: everything has to fit inside it
     const Sizes sz = compute_sizes(*cfg, b->score_bytes, b->size_bytes, b->msa, b->tb_mode, b->trace_bytes);
     if (avail < sz.dev_per_poa + (cfg->band_mode == GWB200_POA_FULL_BAND ? 0 : sz.dev_per_matrix) || sz.dev_per_poa + sz.dev_per_matrix <= 0)
     {
@@ -656,9 +681,21 @@ int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* str
     }
     // ---- device block
     {
-        const int64_t fixed   = 4096 * 2 + 256 * 64;
+        const int64_t fixed   = fixed_dev;
         const int64_t total_d = n * (sz.dev_per_poa + sz.dev_per_matrix) + fixed;
-        if (cudaMalloc(reinterpret_cast<void**>(&b->d_block), total_d) != cudaSuccess)
+        if (ext_block)
+        {
+            if (total_d > ext_bytes)
+            {
+                std::string msg = "Requires at least " + std::to_string(total_d) + " bytes of device memory per CUDAPOA batch to process correctly.";
+                cudaFreeHost(b->h_block);
+                delete b;
+                return set_error(GWB200_E_RUNTIME, msg.c_str());
+            }
+            b->d_block     = static_cast<uint8_t*>(ext_block);
+            b->owns_dblock = false;
+        }
+        else if (cudaMalloc(reinterpret_cast<void**>(&b->d_block), total_d) != cudaSuccess)
         {
             cudaGetLastError();
             cudaFreeHost(b->h_block);
@@ -780,7 +817,7 @@ void gwb200_poa_batch_destroy(gwb200_poa_batch* b)
         cudaEventDestroy(b->ev0);
     if (b->ev1)
         cudaEventDestroy(b->ev1);
-    if (b->d_block)
+    if (b->d_block && b->owns_dblock)
         cudaFree(b->d_block);
     if (b->h_block)
         cudaFreeHost(b->h_block);

@@ -1466,6 +1466,139 @@ __device__ int32_t traceback_tma(const Win<SizeT>& g, const int32_t graph_count,
     return aligned_nodes;
 }
 
+// topologicalSortDeviceUtil (cudapoa_topsort.cuh:45-97): same Kahn FIFO order (the order is observable: rank <-> DP row).
+// Staging (all lanes, coalesced): in-degree counters (u8) into the shared-memory pool, and one packed record per node
+// {min(out-degree, 3), first child, second child} into a per-window scratch array in global memory (32 bits for 16-bit node ids,
+// 64 bits otherwise) that the walk reads sequentially-local (chains run along consecutive node ids: one L1 miss per line).
+// Walk (lane 0): one record load + one counter update per edge; the two front entries of the FIFO live in registers (a bubble
+// keeps two branches interleaved in the queue), later entries in a 64-entry tagged window in shared memory, the rest is read
+// back from sorted[]. Nodes with more than two children read their further children from the adjacency arrays.
+template <typename SizeT>
+__device__ void topsort_v3(const Win<SizeT>& g, const int32_t node_count, uint8_t* pool, const int32_t pool_bytes, void* scratch)
+{
+    constexpr bool kSmall = sizeof(SizeT) == 2;
+    constexpr int32_t kQ  = 64;
+    const int32_t lane    = threadIdx.x & 31;
+    int32_t* q_tag        = reinterpret_cast<int32_t*>(pool);
+    int32_t* q_node       = q_tag + kQ;
+    uint8_t* cnt          = pool + kQ * 8;
+    // counters of the nodes that do not fit the pool live in local_cnt (global memory)
+    const int32_t n_smem  = max(0, min(node_count, pool_bytes - kQ * 8 - 16));
+    uint32_t* rec32       = static_cast<uint32_t*>(scratch);
+    uint2* rec64          = static_cast<uint2*>(scratch);
+
+    for (int32_t k = lane; k < kQ; k += 32)
+        q_tag[k] = -1;
+    __syncwarp();
+    int32_t p = 0;
+    for (int32_t n0 = 0; n0 < node_count; n0 += 32)
+    {
+        const int32_t n = n0 + lane;
+        int32_t c       = 1;
+        if (n < node_count)
+        {
+            c                = g.in_cnt[n];
+            const int32_t oc = g.out_cnt[n];
+            const int32_t e0 = oc >= 1 ? static_cast<int32_t>(g.out_edge(n, 0)) : 0;
+            const int32_t e1 = oc >= 2 ? static_cast<int32_t>(g.out_edge(n, 1)) : 0;
+            if (n < n_smem)
+                cnt[n] = static_cast<uint8_t>(c);
+            else
+                g.local_cnt[n] = static_cast<uint16_t>(c);
+            if (kSmall)
+                rec32[n] = static_cast<uint32_t>(min(oc, 3)) | (static_cast<uint32_t>(e0 & 0x7fff) << 2) | (static_cast<uint32_t>(e1 & 0x7fff) << 17);
+            else
+                rec64[n] = make_uint2(static_cast<uint32_t>(e0) | (static_cast<uint32_t>(min(oc, 3)) << 30), static_cast<uint32_t>(e1));
+        }
+        const bool is_src = n < node_count && c == 0;
+        const uint32_t m  = __ballot_sync(kFull, is_src);
+        if (is_src)
+        {
+            const int32_t at = p + __popc(m & ((1u << lane) - 1));
+            g.pos[n]         = static_cast<SizeT>(at);
+            g.sorted[at]     = static_cast<SizeT>(n);
+            if (at < kQ)
+            {
+                q_node[at] = n;
+                q_tag[at]  = at;
+            }
+        }
+        p += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        int32_t n  = 0;          // next position of sorted[] to process
+        int32_t r0 = -1, r1 = -1; // nodes at positions n and n + 1 when known
+        auto visit = [&](const int32_t child) {
+            int32_t c;
+            if (child < n_smem)
+            {
+                c          = static_cast<int32_t>(cnt[child]) - 1;
+                cnt[child] = static_cast<uint8_t>(c);
+            }
+            else
+            {
+                c                  = static_cast<int32_t>(g.local_cnt[child]) - 1;
+                g.local_cnt[child] = static_cast<uint16_t>(c);
+            }
+            if (c == 0)
+            {
+                g.pos[child] = static_cast<SizeT>(p);
+                g.sorted[p]  = static_cast<SizeT>(child);
+                if (p == n)
+                    r0 = child;
+                else if (p == n + 1)
+                    r1 = child;
+                else if (p - kQ < n) // slot p % kQ held position p - kQ, already consumed
+                {
+                    q_node[p & (kQ - 1)] = child;
+                    q_tag[p & (kQ - 1)]  = p;
+                }
+                p++;
+            }
+        };
+        while (n < p)
+        {
+            int32_t node = r0;
+            if (node < 0)
+            {
+                const int32_t slot = n & (kQ - 1);
+                node               = (q_tag[slot] == n) ? q_node[slot] : static_cast<int32_t>(g.sorted[n]);
+            }
+            r0 = r1;
+            r1 = -1;
+            n++;
+            int32_t oc2, c0, c1;
+            if (kSmall)
+            {
+                const uint32_t r = rec32[node];
+                oc2              = static_cast<int32_t>(r & 3u);
+                c0               = static_cast<int32_t>((r >> 2) & 0x7fffu);
+                c1               = static_cast<int32_t>(r >> 17);
+            }
+            else
+            {
+                const uint2 r = rec64[node];
+                oc2           = static_cast<int32_t>(r.x >> 30);
+                c0            = static_cast<int32_t>(r.x & 0x3fffffffu);
+                c1            = static_cast<int32_t>(r.y);
+            }
+            if (oc2 >= 1)
+                visit(c0);
+            if (oc2 >= 2)
+                visit(c1);
+            if (oc2 == 3)
+            {
+                const int32_t oc = g.out_cnt[node];
+                for (int32_t e = 2; e < oc; e++)
+                    visit(static_cast<int32_t>(g.out_edge(node, e)));
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // needlemanWunschBanded (cudapoa_nw_banded.cuh:177-557) for one warp: band geometry as in nw_banded_v2, rows by dp_rows_v3,
 // end cell + traceback by traceback_tma (or traceback_plain when the pool is too small for the tile buffers).
 template <typename ScoreT, typename SizeT, bool BULK>
@@ -1665,7 +1798,7 @@ __device__ void process_window_v3(const DeviceParams& P, const V2Extra& X, const
                 error      = add_alignment_v2<SizeT>(g, nc, alen, aln_graph, sequence, seq_len, aln_read, base_weights, path, rd_node);
                 GWB200_TIMER_LAP(3);
                 if (!error)
-                    topsort_v2<SizeT>(g, nc, pool, X.pool_bytes, static_cast<SizeT*>(P.cons_preds) + w * mn);
+                    topsort_v3<SizeT>(g, nc, pool, X.pool_bytes, row_meta); // row_meta is free between traceback and the next rows
                 GWB200_TIMER_LAP(4);
                 node_count = nc;
                 if (error)

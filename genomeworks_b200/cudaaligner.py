@@ -51,6 +51,14 @@ def _cigar(actions, runs, extended=False):
     return "".join(out)
 
 
+_RC_LOOKUP = b"TGAC"
+
+
+def _revcomp(seq):
+    """genomeutils::reverse_complement (utils/genomeutils.hpp:144-154): lookup by (c >> 1) & 3 over the reversed sequence."""
+    return bytes(_RC_LOOKUP[(c >> 1) & 3] for c in reversed(seq))
+
+
 class Alignment:
     """What cudaaligner::Alignment exposes (alignment.hpp:55-111)."""
 
@@ -61,6 +69,12 @@ class Alignment:
         self.is_optimal = bool(is_optimal)
         self.actions = actions
         self.runlengths = runs
+
+    def get_query_sequence(self):
+        return self.query
+
+    def get_target_sequence(self):
+        return self.target
 
     def convert_to_cigar(self, extended=False):
         return _cigar(self.actions, self.runlengths, extended)
@@ -136,7 +150,9 @@ class FixedBandAligner:
                                                       C.c_int32(1 if reverse_complement_query else 0),
                                                       C.c_int32(1 if reverse_complement_target else 0)))
         if rc == success:
-            self._pairs.append((q, t))
+            # the Alignment carries the sequences as aligned (after the reverse complement the flags ask for), as the reference
+            # builds it from its staging copy (aligner_global_myers_banded.cpp:226-227,413-418)
+            self._pairs.append((_revcomp(q) if reverse_complement_query else q, _revcomp(t) if reverse_complement_target else t))
         return rc
 
     def align_all(self):

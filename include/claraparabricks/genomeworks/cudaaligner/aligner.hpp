@@ -77,6 +77,20 @@ public:
     {
         check(gwb200_aligner_create(&h_, max_bandwidth, stream, device_id, max_device_memory));
     }
+    /// Every device buffer of the aligner is a block of the caller's allocator (aligner.hpp:183,208; cudaaligner/src/aligner.cpp:76-124).
+    AlignerB200(int32_t max_bandwidth, cudaStream_t stream, int32_t device_id, DefaultDeviceAllocator allocator, int64_t max_device_memory,
+                int32_t max_query = -1, int32_t max_target = -1, int32_t max_alignments = -1)
+        : stream_(stream)
+        , device_(device_id)
+        , mem_(max_device_memory)
+        , max_query_(max_query)
+        , max_target_(max_target)
+        , max_alignments_(max_alignments)
+        , allocator_(allocator)
+    {
+        check(gwb200_aligner_create_with_allocator(&h_, max_bandwidth, stream, device_id, max_device_memory, &AlignerB200::pool_alloc,
+                                                   &AlignerB200::pool_free, this));
+    }
     ~AlignerB200() override { gwb200_aligner_destroy(h_); }
     AlignerB200(const AlignerB200&) = delete;
     AlignerB200& operator=(const AlignerB200&) = delete;
@@ -89,32 +103,83 @@ public:
     StatusType add_alignment(int32_t max_bandwidth, const char* query, int32_t query_length, const char* target, int32_t target_length,
                              bool rc_q = false, bool rc_t = false) override
     {
-        if (max_query_ >= 0 && (query_length > max_query_ || target_length > max_target_))
-            return StatusType::exceeded_max_length; // AlignerGlobal::add_alignment, cudaaligner/src/aligner_global.cpp:50-86
-        if (max_alignments_ >= 0 && num_alignments() >= max_alignments_)
-            return StatusType::exceeded_max_alignments;
+        if (max_query_ >= 0)
+        {
+            // the deprecated fixed-size factory: AlignerGlobal::add_alignment (cudaaligner/src/aligner_global.cpp:78-141) -- the
+            // Alignment object exists from here on (get_alignments() lists it before sync_alignments() fills it in)
+            if (query_length < 0 || target_length < 0)
+                return StatusType::generic_error;
+            if (static_cast<int32_t>(alignments_.size()) >= max_alignments_)
+                return StatusType::exceeded_max_alignments;
+            if (query_length > max_query_ || target_length > max_target_)
+                return StatusType::exceeded_max_length;
+        }
         const int rc = check(gwb200_aligner_add_alignment(h_, max_bandwidth, query, query_length, target, target_length, rc_q ? 1 : 0, rc_t ? 1 : 0));
         if (rc == success)
-            pending_.emplace_back(std::string(query, query + query_length), std::string(target, target + target_length));
+        {
+            // the Alignment carries the sequences as they were aligned, i.e. after the reverse complement the flags ask for
+            // (the reference builds it from its staging copy, aligner_global_myers_banded.cpp:226-227,413-418)
+            if (max_query_ >= 0)
+            {
+                auto al = std::make_shared<AlignmentB200>(staged(query, query_length, rc_q), staged(target, target_length, rc_t));
+                al->set_type(AlignmentType::global_alignment);
+                alignments_.push_back(std::move(al));
+            }
+            else
+            {
+                pending_.emplace_back(staged(query, query_length, rc_q), staged(target, target_length, rc_t));
+            }
+        }
         return static_cast<StatusType>(rc);
+    }
+    static std::string staged(const char* seq, int32_t length, bool reverse_complement)
+    {
+        std::string out(seq, seq + length);
+        if (reverse_complement)
+        {
+            // genomeutils::reverse_complement (utils/genomeutils.hpp:144-154): A -> T, C -> G, T -> A, G -> C by (c >> 1) & 3
+            static const char lookup[4] = {'T', 'G', 'A', 'C'};
+            for (int32_t pos = 0; pos < length; ++pos)
+                out[pos] = lookup[(static_cast<unsigned char>(seq[length - 1 - pos]) >> 1) & 0x3];
+        }
+        return out;
     }
     StatusType align_all() override { return static_cast<StatusType>(check(gwb200_aligner_align_all(h_))); }
     StatusType sync_alignments() override
     {
         const int rc = check(gwb200_aligner_sync_alignments(h_));
+        auto fetch = [&](int32_t i, AlignmentB200& al) {
+            int32_t st = 0, opt = 0, n = 0;
+            check(gwb200_aligner_result_info(h_, i, &st, &opt, &n));
+            std::vector<int8_t> a(std::max(n, 1));
+            std::vector<int32_t> r(std::max(n, 1));
+            check(gwb200_aligner_result_runs(h_, i, a.data(), r.data()));
+            a.resize(n);
+            r.resize(n);
+            if (st == success)
+                al.set(StatusType::success, opt != 0, std::move(a), std::move(r));
+        };
+        if (max_query_ >= 0)
+        {
+            // AlignerGlobal::sync_alignments (aligner_global.cpp:162-190): results are filled into the existing objects
+            const int32_t n_results = gwb200_aligner_num_results(h_);
+            for (int32_t i = first_unsynced_; i < static_cast<int32_t>(alignments_.size()) && i - first_unsynced_ < n_results; ++i)
+            {
+                AlignmentB200* al = static_cast<AlignmentB200*>(alignments_[i].get());
+                fetch(i - first_unsynced_, *al);
+                al->expand();
+            }
+            if (n_results > 0)
+                first_unsynced_ = static_cast<int32_t>(alignments_.size());
+            return static_cast<StatusType>(rc);
+        }
+        if (gwb200_aligner_num_results(h_) == 0 && pending_.empty())
+            return static_cast<StatusType>(rc); // nothing was aligned since the last sync: the previous alignments stay
         alignments_.clear();
         for (size_t i = 0; i < pending_.size(); ++i)
         {
-            int32_t st = 0, opt = 0, n = 0;
-            check(gwb200_aligner_result_info(h_, static_cast<int32_t>(i), &st, &opt, &n));
-            std::vector<int8_t> a(std::max(n, 1));
-            std::vector<int32_t> r(std::max(n, 1));
-            check(gwb200_aligner_result_runs(h_, static_cast<int32_t>(i), a.data(), r.data()));
-            a.resize(n);
-            r.resize(n);
             auto al = std::make_shared<AlignmentB200>(std::move(pending_[i].first), std::move(pending_[i].second));
-            if (st == success)
-                al->set(StatusType::success, opt != 0, std::move(a), std::move(r));
+            fetch(static_cast<int32_t>(i), *al);
             alignments_.push_back(std::move(al));
         }
         pending_.clear();
@@ -133,6 +198,7 @@ public:
         check(gwb200_aligner_reset(h_));
         pending_.clear();
         alignments_.clear();
+        first_unsynced_ = 0;
     }
     void reset_max_bandwidth(int32_t max_bandwidth) override
     {
@@ -141,17 +207,41 @@ public:
         alignments_.clear();
     }
     void free_temporary_device_buffers() override { check(gwb200_aligner_free_temporary_device_buffers(h_)); }
-    int32_t num_alignments() const override { return gwb200_aligner_num_alignments(h_); }
+    int32_t num_alignments() const override
+    {
+        return max_query_ >= 0 ? static_cast<int32_t>(alignments_.size()) : gwb200_aligner_num_alignments(h_);
+    }
     cudaStream_t get_stream() const override { return stream_; }
     int32_t get_device() const override { return device_; }
-    DefaultDeviceAllocator get_device_allocator() const override { return DefaultDeviceAllocator(mem_, stream_); }
+    /// The allocator the aligner was created with; an aligner created without one allocates with cudaMalloc directly and
+    /// returns a default-constructed allocator (no pool).
+    DefaultDeviceAllocator get_device_allocator() const override { return allocator_; }
 
 private:
+    static void* pool_alloc(void* user, int64_t bytes)
+    {
+        AlignerB200* self = static_cast<AlignerB200*>(user);
+        try
+        {
+            return self->allocator_.allocate(static_cast<std::size_t>(bytes), {self->stream_});
+        }
+        catch (const device_memory_allocation_exception&)
+        {
+            return nullptr;
+        }
+    }
+    static void pool_free(void* user, void* ptr, int64_t bytes)
+    {
+        static_cast<AlignerB200*>(user)->allocator_.deallocate(static_cast<char*>(ptr), static_cast<std::size_t>(bytes));
+    }
+
     gwb200_aligner* h_ = nullptr;
     cudaStream_t stream_;
     int32_t device_;
     int64_t mem_;
     int32_t max_query_, max_target_, max_alignments_;
+    DefaultDeviceAllocator allocator_;
+    int32_t first_unsynced_ = 0; // deprecated factory: first alignment that has no result yet
     std::vector<std::pair<std::string, std::string>> pending_;
     std::vector<std::shared_ptr<Alignment>> alignments_;
 };
@@ -172,7 +262,7 @@ inline std::unique_ptr<Aligner> create_aligner(int32_t max_query_length, int32_t
     if (type != AlignmentType::global_alignment)
         throw std::runtime_error("Aligner for specified type not implemented yet.");
     return std::unique_ptr<Aligner>(new detail::AlignerB200(detail::covering_bandwidth(max_query_length, max_target_length), stream, device_id,
-                                                            allocator.get_size_of_largest_free_memory_block(), max_query_length,
+                                                            allocator, allocator.get_size_of_largest_free_memory_block(), max_query_length,
                                                             max_target_length, max_alignments));
 }
 /// Deprecated factory (aligner.hpp:196).
@@ -197,7 +287,7 @@ inline std::unique_ptr<FixedBandAligner> create_aligner(AlignmentType type, int3
         throw std::invalid_argument("max_device_memory has to be either -1 (=all available GPU memory) or greater or equal than 0.");
     if (max_device_memory == -1)
         max_device_memory = allocator.get_size_of_largest_free_memory_block();
-    return std::unique_ptr<FixedBandAligner>(new detail::AlignerB200(max_bandwidth, stream, device_id, max_device_memory));
+    return std::unique_ptr<FixedBandAligner>(new detail::AlignerB200(max_bandwidth, stream, device_id, allocator, max_device_memory));
 }
 /// FixedBand factory (aligner.hpp:219).
 inline std::unique_ptr<FixedBandAligner> create_aligner(AlignmentType type, int32_t max_bandwidth, cudaStream_t stream, int32_t device_id,

@@ -60,6 +60,7 @@ public:
         , target_(std::move(t))
     {
     }
+    void set_type(AlignmentType t) { type_ = t; }
     void set(StatusType st, bool optimal, std::vector<int8_t> actions, std::vector<int32_t> runs)
     {
         status_     = st;
@@ -67,6 +68,13 @@ public:
         actions_    = std::move(actions);
         runs_       = std::move(runs);
         type_       = AlignmentType::global_alignment;
+    }
+    /// AlignerGlobal results are one AlignmentState per step (aligner_global.cpp:162-190), not run-length encoded
+    void expand()
+    {
+        expanded_.clear();
+        for (size_t k = 0; k < actions_.size(); ++k)
+            expanded_.insert(expanded_.end(), static_cast<size_t>(runs_[k]), static_cast<AlignmentState>(actions_[k]));
     }
     const std::string& get_query_sequence() const override { return query_; }
     const std::string& get_target_sequence() const override { return target_; }

@@ -116,7 +116,33 @@ public:
         const gwb200_poa_config c = cfg.to_c();
         check(gwb200_poa_batch_create(&h_, device_id, stream, max_gpu_mem, output_mask, &c, gap_score, mismatch_score, match_score));
     }
-    ~BatchB200() override { gwb200_poa_batch_destroy(h_); }
+    /// The whole batch lives in one block of the caller's allocator (batch.hpp:176-189; allocate_block.hpp:48-100 takes its
+    /// device buffer from the allocator the same way). The block goes back to the pool when the batch is destroyed.
+    BatchB200(int32_t device_id, cudaStream_t stream, DefaultDeviceAllocator allocator, int64_t block_bytes, int8_t output_mask,
+              const BatchConfig& cfg, int16_t gap_score, int16_t mismatch_score, int16_t match_score)
+        : cfg_(cfg)
+        , allocator_(allocator)
+        , block_bytes_(block_bytes)
+    {
+        const gwb200_poa_config c = cfg.to_c();
+        block_                    = allocator_.allocate(static_cast<std::size_t>(block_bytes_), {stream});
+        try
+        {
+            check(gwb200_poa_batch_create_in_block(&h_, device_id, stream, block_, block_bytes_, output_mask, &c, gap_score, mismatch_score,
+                                                   match_score));
+        }
+        catch (...)
+        {
+            allocator_.deallocate(block_, static_cast<std::size_t>(block_bytes_));
+            throw;
+        }
+    }
+    ~BatchB200() override
+    {
+        gwb200_poa_batch_destroy(h_);
+        if (block_ != nullptr)
+            allocator_.deallocate(block_, static_cast<std::size_t>(block_bytes_));
+    }
     BatchB200(const BatchB200&) = delete;
     BatchB200& operator=(const BatchB200&) = delete;
 
@@ -219,6 +245,9 @@ public:
 private:
     gwb200_poa_batch* h_ = nullptr;
     BatchConfig cfg_;
+    DefaultDeviceAllocator allocator_; // default constructed (no pool) unless the batch was created with an allocator
+    char* block_         = nullptr;
+    int64_t block_bytes_ = 0;
 };
 } // namespace detail
 
@@ -231,7 +260,8 @@ inline std::unique_ptr<Batch> create_batch(int32_t device_id, cudaStream_t strea
         throw std::invalid_argument("max_gpu_mem has to be either -1 (=all available GPU memory) or greater or equal than 0.");
     if (max_gpu_mem == -1)
         max_gpu_mem = allocator.get_size_of_largest_free_memory_block();
-    return std::unique_ptr<Batch>(new detail::BatchB200(device_id, stream, max_gpu_mem, output_mask, batch_size, gap_score, mismatch_score, match_score));
+    return std::unique_ptr<Batch>(
+        new detail::BatchB200(device_id, stream, allocator, max_gpu_mem, output_mask, batch_size, gap_score, mismatch_score, match_score));
 }
 
 /// create_batch (batch.hpp:191-204); note the reference's argument order: gap, mismatch, match.

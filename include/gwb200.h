@@ -118,6 +118,12 @@ typedef struct gwb200_poa_batch gwb200_poa_batch; /* opaque: one cudapoa::Batch 
  * Too little memory for one window => GWB200_E_RUNTIME (allocate_block.hpp:67-73). */
 int gwb200_poa_batch_create(gwb200_poa_batch** out, int32_t device_id, void* stream, int64_t max_gpu_mem, int8_t output_mask,
                             const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score, int16_t match_score);
+/* create_batch(device_id, stream, DefaultDeviceAllocator allocator, max_gpu_mem, ...) -- batch.hpp:176-189, batch.cu:106-232,
+ * allocate_block.hpp:48-100: the batch lives entirely inside `device_block` (a 256-byte aligned block of device_block_bytes
+ * bytes the caller took from its allocator and releases after gwb200_poa_batch_destroy); nothing else is allocated on the device. */
+int gwb200_poa_batch_create_in_block(gwb200_poa_batch** out, int32_t device_id, void* stream, void* device_block, int64_t device_block_bytes,
+                                     int8_t output_mask, const gwb200_poa_config* cfg, int16_t gap_score, int16_t mismatch_score,
+                                     int16_t match_score);
 void gwb200_poa_batch_destroy(gwb200_poa_batch* batch);
 
 /* Batch::add_poa_group(per_seq_status, poa_group) -- batch.hpp:100-111, cudapoa_batch.cuh:103-151.
@@ -214,6 +220,13 @@ int gwb200_aligner_init(void);
  * < -1 => GWB200_E_INVALID_ARGUMENT; max_bandwidth % 32 == 1 => GWB200_E_INVALID_ARGUMENT
  * (aligner_global_myers_banded.cpp:470-473). */
 int gwb200_aligner_create(gwb200_aligner** out, int32_t max_bandwidth, void* stream, int32_t device_id, int64_t max_device_memory);
+/* create_aligner(..., DefaultDeviceAllocator allocator, max_device_memory) -- aligner.hpp:183-219, cudaaligner/src/aligner.cpp:76-124:
+ * every device buffer of the aligner is a block of the caller's allocator (allocator.hpp:322-358). alloc_fn returns NULL when
+ * the pool cannot serve the request (the alignment call then fails the way an out-of-memory does); free_fn gets the size back. */
+typedef void* (*gwb200_device_alloc_fn)(void* user, int64_t bytes);
+typedef void (*gwb200_device_free_fn)(void* user, void* ptr, int64_t bytes);
+int gwb200_aligner_create_with_allocator(gwb200_aligner** out, int32_t max_bandwidth, void* stream, int32_t device_id, int64_t max_device_memory,
+                                         gwb200_device_alloc_fn alloc_fn, gwb200_device_free_fn free_fn, void* user);
 void gwb200_aligner_destroy(gwb200_aligner* aligner);
 /* FixedBandAligner::add_alignment([max_bandwidth,] query, query_length, target, target_length, rc_query, rc_target)
  * -- aligner.hpp:96-97,158-170; aligner_global_myers_banded.cpp:155-258. max_bandwidth <= 0 => the aligner's own. */
@@ -225,6 +238,8 @@ int gwb200_aligner_align_all(gwb200_aligner* aligner);
 int gwb200_aligner_sync_alignments(gwb200_aligner* aligner);
 /* Aligner::num_alignments(), aligner.hpp:128 */
 int32_t gwb200_aligner_num_alignments(const gwb200_aligner* aligner);
+/* number of results the last sync_alignments() produced (what get_alignments() can be filled from) */
+int32_t gwb200_aligner_num_results(const gwb200_aligner* aligner);
 /* Results of alignment i after sync (what Alignment::get_status / is_optimal / get_actions / get_runlengths expose,
  * alignment.hpp:55-111): status, is_optimal, number of run-length entries; then the entries themselves
  * (actions: AlignmentState bytes, runlengths), query-start to query-end order. */

@@ -5,6 +5,7 @@
 #include <claraparabricks/genomeworks/cudaaligner/alignment.hpp>
 #include <claraparabricks/genomeworks/cudapoa/batch.hpp>
 #include <claraparabricks/genomeworks/cudapoa/cudapoa.hpp>
+#include <claraparabricks/genomeworks/utils/allocator.hpp>
 #include <claraparabricks/genomeworks/utils/genomeutils.hpp>
 
 #include <cstdio>
@@ -140,9 +141,76 @@ int main()
         auto legacy = cudaaligner::create_aligner(10, 10, 2, cudaaligner::AlignmentType::global_alignment, nullptr, 0, 1ll << 30);
         REQUIRE(legacy->add_alignment("AAATC", 5, "TACGTTTT", 8) == cudaaligner::StatusType::success);
         REQUIRE(legacy->add_alignment("AAAAAAAAAAA", 11, "A", 1) == cudaaligner::StatusType::exceeded_max_length);
+        // AlignerGlobal semantics (aligner_global.cpp:78-141,162-190), which the Cython shim relies on (cudaaligner.pyx:237-243):
+        // the Alignment exists from add_alignment() on and sync_alignments() fills it in place
+        REQUIRE(legacy->get_alignments().size() == 1 && legacy->num_alignments() == 1);
+        std::shared_ptr<cudaaligner::Alignment> before = legacy->get_alignments()[0];
+        REQUIRE(before->get_status() == cudaaligner::StatusType::uninitialized);
         legacy->align_all();
         legacy->sync_alignments();
-        REQUIRE(legacy->get_alignments()[0]->convert_to_cigar() == "3M1I2M2I");
+        REQUIRE(legacy->get_alignments()[0] == before && before->get_status() == cudaaligner::StatusType::success);
+        REQUIRE(before->convert_to_cigar() == "3M1I2M2I");
+        REQUIRE(before->get_alignment().size() == 8); // one AlignmentState per step
+        REQUIRE(legacy->add_alignment("TGCA", 4, "ATACGCT", 7) == cudaaligner::StatusType::success);
+        REQUIRE(legacy->add_alignment("TGCA", 4, "ATACGCT", 7) == cudaaligner::StatusType::exceeded_max_alignments);
+        legacy->align_all();
+        legacy->sync_alignments();
+        REQUIRE(legacy->get_alignments().size() == 2 && legacy->get_alignments()[1]->convert_to_cigar() == "1I1M2I3M");
+        legacy->reset();
+        REQUIRE(legacy->get_alignments().empty());
+    }
+    // ---- the allocator that is part of the API (utils/allocator.hpp:208-358): one pool, copies share it, Batch and Aligner carve from it
+    {
+        DefaultDeviceAllocator alloc = create_default_device_allocator(3ull << 30);
+        const int64_t whole          = get_size_of_largest_free_memory_block(alloc);
+        REQUIRE(whole >= (3ll << 30) - 256);
+        DefaultDeviceAllocator copy = alloc;
+        char* p                     = copy.allocate(1 << 20);
+        REQUIRE(p != nullptr && alloc.get_size_of_largest_free_memory_block() == whole - (1 << 20));
+        CachingDeviceAllocator<int32_t, details::DevicePreallocatedAllocator> rebound(alloc);
+        int32_t* q = rebound.allocate(256);
+        REQUIRE(reinterpret_cast<char*>(q) == p + (1 << 20));
+        rebound.deallocate(q, 256);
+        copy.deallocate(p, 1 << 20);
+        REQUIRE(alloc.get_size_of_largest_free_memory_block() == whole);
+        REQUIRE(alloc.memory_resource() == copy.memory_resource());
+        {
+            cudapoa::BatchConfig cfg(1024, 10, 256, cudapoa::BandMode::static_band);
+            auto b1 = cudapoa::create_batch(0, nullptr, alloc, 1ll << 30, cudapoa::OutputType::consensus, cfg, -8, -6, 8);
+            auto b2 = cudapoa::create_batch(0, nullptr, alloc, 1ll << 30, cudapoa::OutputType::consensus, cfg, -8, -6, 8);
+            REQUIRE(alloc.get_size_of_largest_free_memory_block() == whole - (2ll << 30)); // two batches, two disjoint blocks
+            bool threw = false;
+            try
+            {
+                cudapoa::create_batch(0, nullptr, alloc, 2ll << 30, cudapoa::OutputType::consensus, cfg, -8, -6, 8);
+            }
+            catch (const device_memory_allocation_exception&)
+            {
+                threw = true;
+            }
+            REQUIRE(threw);
+            std::string a(500, 'C');
+            cudapoa::Group g;
+            for (int i = 0; i < 4; i++)
+                g.push_back(cudapoa::Entry{a.c_str(), nullptr, static_cast<int32_t>(a.size())});
+            std::vector<cudapoa::StatusType> per_seq, st;
+            REQUIRE(b1->add_poa_group(per_seq, g) == cudapoa::StatusType::success);
+            REQUIRE(b2->add_poa_group(per_seq, g) == cudapoa::StatusType::success);
+            b1->generate_poa();
+            b2->generate_poa();
+            std::vector<std::string> cons;
+            std::vector<std::vector<uint16_t>> cov;
+            REQUIRE(b2->get_consensus(cons, cov, st) == cudapoa::StatusType::success && cons[0] == a);
+            REQUIRE(b1->get_consensus(cons, cov, st) == cudapoa::StatusType::success && cons[1] == a);
+            auto al = cudaaligner::create_aligner(cudaaligner::AlignmentType::global_alignment, 64, nullptr, 0, alloc, -1);
+            REQUIRE(al->add_alignment("AAATC", 5, "TACGTTTT", 8) == cudaaligner::StatusType::success);
+            al->align_all();
+            al->sync_alignments();
+            REQUIRE(al->get_alignments()[0]->convert_to_cigar() == "3M1I2M2I");
+            REQUIRE(al->get_device_allocator().memory_resource() == alloc.memory_resource());
+            REQUIRE(alloc.get_size_of_largest_free_memory_block() < whole - (2ll << 30)); // the aligner's buffers are pool blocks too
+        }
+        REQUIRE(alloc.get_size_of_largest_free_memory_block() == whole); // everything went back to the pool
     }
     std::printf("CPP_API_OK\n");
     return 0;

@@ -174,3 +174,35 @@ def test_aligner_api_contracts():
     b.align_all()
     out = b.get_alignments()
     assert [a.cigar for a in out] == ["3M1I2M2I", "1I1M2I3M"]
+
+
+def test_reverse_complement_flags_travel_with_the_alignment():
+    """add_alignment(..., reverse_complement_query/target): the Alignment's sequences and format_alignment() are those that
+    were aligned (aligner_global_myers_banded.cpp:226-227,413-418), so they agree with the CIGAR."""
+    from genomeworks_b200 import cudaaligner
+    q, t = "AAACCGTTTTGCA", "TGCAAAACGGATT"
+    al = cudaaligner.FixedBandAligner(32)
+    assert al.add_alignment(q, t, reverse_complement_query=True) == cudaaligner.success
+    assert al.add_alignment(q, t, reverse_complement_target=True) == cudaaligner.success
+    al.align_all()
+    al.sync_alignments()
+    r = al.get_alignments()
+    rc = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    q_rc = "".join(rc[c] for c in reversed(q))
+    t_rc = "".join(rc[c] for c in reversed(t))
+    assert r[0].get_query_sequence() == q_rc and r[0].get_target_sequence() == t
+    assert r[1].get_query_sequence() == q and r[1].get_target_sequence() == t_rc
+    # same result as aligning the reverse-complemented strings directly
+    al2 = cudaaligner.FixedBandAligner(32)
+    al2.add_alignment(q_rc, t)
+    al2.add_alignment(q, t_rc)
+    al2.align_all()
+    al2.sync_alignments()
+    r2 = al2.get_alignments()
+    for a, b in zip(r, r2):
+        assert a.convert_to_cigar() == b.convert_to_cigar()
+        assert a.format_alignment() == b.format_alignment()
+        fa = a.format_alignment()
+        assert fa[0].replace("-", "") == a.get_query_sequence() and fa[2].replace("-", "") == a.get_target_sequence()
+    al.close()
+    al2.close()
