@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- the measurement contract.
 
-Metric (BASELINE.json): POA consensus windows/sec on synthetic 10 kb x 32-read windows (config C3: adaptive band 256,
-int32 scores; adaptive_storage_factor 3.0 -- the reference's default 2.0 yields exceeded_adaptive_banded_matrix_size for
-every window of this workload on both this engine and the reference (SURVEY.md fact 3 / DESIGN.md), 3.0 is the smallest
-integer factor at which all windows succeed; the factor only sizes the per-window score slab, results are identical). One "step" = one pass of the hot path over one batch
-of `--windows` windows per GPU. Windows shard embarrassingly: every rank owns a Batch and its own windows (weak scaling),
-NCCL is used only for the barrier / max-over-ranks timing and the result gather after the timed region.
+Metric (BASELINE.json): POA consensus windows/sec on synthetic 10 kb x 32-read windows (config C3: adaptive band 256, int32
+scores; adaptive_storage_factor 3.0 -- the reference's default 2.0 yields exceeded_adaptive_banded_matrix_size for every window
+of this workload on both this engine and the reference (SURVEY.md fact 3 / DESIGN.md), 3.0 is the smallest integer factor at
+which all windows succeed; the factor only sizes the per-window score slab, results are identical). One "step" = one pass of the
+hot path over one batch: as many windows as the Batch holds in HBM (capacity-sized, not rounded to a wave: the kernel runs a
+persistent grid). Windows shard embarrassingly: every rank owns a Batch and its own windows (weak scaling), NCCL is used only
+for the barrier / max-over-ranks timing and the result gather after the timed region (--scaling strong: scatter + gather inside).
 
-  value : windows/s, inputs packed and resident in HBM before the timed region (K x [launch, sync], CUDA events on the
-          batch stream, max over ranks)
-  e2e   : windows/s through the public API with HOST buffers every step: add_poa_group packing, H2D, kernel, D2H of
-          consensus + coverage (wall clock around barrier + synchronize, max over ranks)
-  roofline: algorithmic bytes = executed DP cells x sizeof(ScoreT) / kernel time, vs MEASURED_PEAKS hbm_gbs
-  cpu_baseline / --impl reference: 3rdparty/spoa (oracle/_ref/libspoa_ref.so, unmodified) on the host cores.
+  value : windows/s, inputs packed and resident in HBM before the timed region (K x launch, CUDA events on the batch stream,
+          max over ranks)
+  e2e   : windows/s through the drop-in API with HOST buffers every step: one add_poa_group call per window (packing), H2D,
+          kernel, D2H of consensus + coverage (wall clock around barrier + synchronize, max over ranks)
+  roofline: algorithmic bytes = executed DP cells x sizeof(ScoreT) / kernel time, vs MEASURED_PEAKS hbm_gbs;
+          traffic = dram bytes per window of the shipped kernel from the committed ncu capture (profiles/r02_traffic.json)
+  extra : the other driver-visible workloads on the same line: C3 with MSA output, C2 (1 kb x 16, static band, int16), C4
+          (cudaaligner 10k x 10k, band 1024), each with value / e2e / roofline fraction
+  cpu_baseline / --impl reference: 3rdparty/spoa (oracle/_ref/libspoa_ref.so, unmodified) on the host cores. The reference arm
+          runs FULL 32-read windows: every host thread keeps one window in progress and fuses 2 reads per step, so that after 16
+          steps every read position of a window has been timed against the true graph (oracle/spoa_capi.cpp, streaming interface).
 
-Other workloads for development: --workload c2 (1 kb x 16, static band, 1024 windows), c4 (aligner 10k x 10k, bw 1024).
+Other workloads as the main line for development: --workload c2 | c4.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -32,10 +39,6 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 
-# dram bytes (read + write) per window of the dominant kernel, from the committed ncu --set full captures (profiles/)
-NCU_DRAM_BYTES_PER_WINDOW = {"c3": (1.810265e9 + 15.109566e9) / 16, "c2": (4.804323e9 + 9.375816e9) / 1024}
-
-
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -44,6 +47,16 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes (read + write) per unit of the dominant kernel from the committed ncu --set full capture of the shipped build
+    (profiles/r02_traffic.json, written from gpurun_out/ncu by tools/ncu_traffic.py). None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        return json.load(open(p)).get(workload)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -87,26 +100,29 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def workload_params(name, windows):
+def workload_params(name, windows=0):
     if name == "c3":
-        return dict(kind="poa", name="C3: cudapoa long-read consensus, 10 kb x 32 reads/window, adaptive band 256, int32 scores, "
+        return dict(kind="poa", key="c3", name="C3: cudapoa long-read consensus, 10 kb x 32 reads/window, adaptive band 256, int32 scores, "
                     "adaptive_storage_factor 3.0", backbone=10000, reads=32, mut=200, ins=100, dele=100, max_seq=10240, band=256,
-                    band_mode="adaptive_band", factor=3.0, windows=windows or 296)
+                    band_mode="adaptive_band", factor=3.0, windows=windows)
     if name == "c2":
-        return dict(kind="poa", name="C2: cudapoa short-read consensus, 1 kb x 16 reads/window, static band 256, int16 scores",
+        return dict(kind="poa", key="c2", name="C2: cudapoa short-read consensus, 1 kb x 16 reads/window, static band 256, int16 scores",
                     backbone=1000, reads=16, mut=20, ins=10, dele=10, max_seq=1024, band=256, band_mode="static_band", factor=2.0,
                     windows=windows or 1024)
     if name == "c4":
-        return dict(kind="aligner", name="C4: cudaaligner global, 10000 x 10000 bp, Myers banded (max_bandwidth 1024)", genome=10000,
+        return dict(kind="aligner", key="c4", name="C4: cudaaligner global, 10000 x 10000 bp, Myers banded (max_bandwidth 1024)", genome=10000,
                     max_bw=1024, windows=windows or 512)
     raise SystemExit("unknown workload " + name)
 
 
+# ------------------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes anything under oracle/)
+# ------------------------------------------------------------------------------------------------------------------------------
 def spoa_sample(wp, n_windows, seed0, threads=0, reads=None):
-    """Times unmodified spoa on n_windows windows of the workload. For long-read workloads a full 10 kb x 32-read window costs
-    spoa ~3e9 DP cells (minutes per window per core), so the bounded sample uses the first `reads` reads of each window and
-    the windows/s figure is extrapolated with spoa's own DP-cell count: cells(full window) is estimated from the sample's
-    graph growth (nodes grow linearly with the number of reads fused)."""
+    """Times unmodified spoa on n_windows windows of the workload (bounded sample for `cpu_baseline`). For long-read workloads a
+    full window costs spoa minutes per core, so the sample uses the first `reads` reads of each window and the windows/s figure
+    is extrapolated with spoa's own DP-cell count (graph nodes grow linearly with the number of reads fused). The reference arm
+    (--impl reference) measures full windows instead."""
     import ref_lib
     from genomeworks_b200 import synth
     full_reads = wp["reads"]
@@ -114,14 +130,11 @@ def spoa_sample(wp, n_windows, seed0, threads=0, reads=None):
     win_nseq, seq_len, data = synth.poa_windows(n_windows, wp["backbone"], full_reads, wp["mut"], wp["ins"], wp["dele"], seed0=seed0,
                                                 max_read_len=wp["max_seq"])
     if reads < full_reads:
-        # keep the first `reads` reads of every window
         sl = seq_len.reshape(n_windows, full_reads)
         offs = np.concatenate([[0], np.cumsum(seq_len)]).astype(np.int64)
         keep = []
         for w in range(n_windows):
-            b = int(offs[w * full_reads])
-            e = int(offs[w * full_reads + reads])
-            keep.append(data[b:e])
+            keep.append(data[int(offs[w * full_reads]):int(offs[w * full_reads + reads])])
         data = np.concatenate(keep + [np.zeros(1, np.uint8)])
         seq_len = np.ascontiguousarray(sl[:, :reads]).reshape(-1)
         win_nseq = np.full(n_windows, reads, dtype=np.int32)
@@ -130,7 +143,6 @@ def spoa_sample(wp, n_windows, seed0, threads=0, reads=None):
     r["reads_used"] = reads
     L = float(wp["backbone"])
     if reads < full_reads:
-        # spoa cells = sum_r nodes_r * len_r; nodes_r ~ L * (1 + g * (r - 1)) with growth g fitted on the sample
         a = reads - 1
         cells_pw = r["cells"] / n_windows
         g = max(0.0, (cells_pw / (L * L) - a) / max(a * (a - 1) / 2.0, 1e-9))
@@ -143,9 +155,92 @@ def spoa_sample(wp, n_windows, seed0, threads=0, reads=None):
     return r
 
 
+def spoa_full_window_stream(wp, steps, warmup, reads_per_step=2):
+    """Reference arm for long-read workloads: full windows through the streaming interface. Returns (value windows/s, info dict)."""
+    import ref_lib
+    from genomeworks_b200 import synth
+    cores = os.cpu_count() or 1
+    lib = ref_lib.spoa()
+    lib.spoa_stream_create.restype = C.c_void_p
+    lib.spoa_stream_step.restype = C.c_double
+    n_threads = max(1, min(cores, 256))
+    n_windows = 3 * n_threads
+    win_nseq, seq_len, data = synth.poa_windows(n_windows, wp["backbone"], wp["reads"], wp["mut"], wp["ins"], wp["dele"], seed0=1000,
+                                                max_read_len=wp["max_seq"])
+    h = C.c_void_p(lib.spoa_stream_create(C.c_int32(n_windows), win_nseq.ctypes.data_as(C.c_void_p), seq_len.ctypes.data_as(C.c_void_p),
+                                          data.ctypes.data_as(C.c_void_p), C.c_int32(8), C.c_int32(-6), C.c_int32(-8), C.c_int32(n_threads)))
+    P = wp["reads"]
+    sec = np.zeros(P, dtype=np.float64)
+    cel = np.zeros(P, dtype=np.float64)
+    cnt = np.zeros(P, dtype=np.int64)
+    done = C.c_int64(0)
+    step_s = []
+    for it in range(warmup + steps):
+        if it == warmup:
+            sec[:], cel[:], cnt[:] = 0, 0, 0
+        s = lib.spoa_stream_step(h, C.c_int32(reads_per_step), C.c_int32(P), sec.ctypes.data_as(C.c_void_p), cel.ctypes.data_as(C.c_void_p),
+                                 cnt.ctypes.data_as(C.c_void_p), C.byref(done))
+        if it >= warmup:
+            step_s.append(float(s))
+    lib.spoa_stream_destroy(h)
+    measured = cnt > 0
+    per_pos = np.zeros(P)
+    per_pos[measured] = sec[measured] / cnt[measured]
+    if measured.sum() >= 2 and not measured.all():
+        # positions the timed steps did not reach: straight line through the measured ones (alignment cost grows with the graph)
+        xs = np.nonzero(measured)[0]
+        b, a = np.polyfit(xs[xs > 0] if (xs > 0).sum() >= 2 else xs, per_pos[xs[xs > 0]] if (xs > 0).sum() >= 2 else per_pos[xs], 1)
+        for p in np.nonzero(~measured)[0]:
+            per_pos[p] = max(0.0, a + b * p) if p > 0 else 0.0
+    t_window = float(per_pos.sum())
+    value = n_threads / t_window if t_window > 0 else 0.0
+    info = {"threads": n_threads, "reads_per_step": reads_per_step, "positions_measured": int(measured.sum()), "positions": int(P),
+            "seconds_per_window_per_thread": t_window, "spoa_dp_cells_per_s": float(cel.sum() / max(sec.sum(), 1e-9) * n_threads),
+            "windows_completed": int(done.value), "step_seconds": step_s}
+    return value, info
+
+
+def gpu_reference_leg(wp, n_windows):
+    """The UNMODIFIED reference GPU kernels (oracle/_ref/libgwref.so, rebuilt for sm_100a) on a bounded sample of the same
+    workload, next to this engine on the same inputs with an identical-output check. Part of the reference
+    arm's line only."""
+    import ref_lib
+    import torch
+    from genomeworks_b200 import cudapoa, synth
+    if not (ref_lib.have_gwref() and torch.cuda.is_available()):
+        return {"unavailable": "oracle/_ref/libgwref.so not built or no CUDA device"}
+    win_nseq, seq_len, data = synth.poa_windows(n_windows, wp["backbone"], wp["reads"], wp["mut"], wp["ins"], wp["dele"], seed0=1000,
+                                                max_read_len=wp["max_seq"])
+    bm = {"full_band": 0, "static_band": 1, "adaptive_band": 2}[wp["band_mode"]]
+    best = None
+    for _ in range(2):  # first call warms the reference's context up
+        r = ref_lib.ref_poa_run(win_nseq, seq_len, data, wp["max_seq"], wp["reads"], wp["band"], bm, adaptive_storage_factor=wp["factor"],
+                                mem_fraction=0.45, max_windows_per_batch=n_windows)
+        ms = float(r["timings"][1])
+        best = ms if best is None else min(best, ms)
+    cfg = cudapoa.make_config(wp["max_seq"], wp["reads"], wp["band"], wp["band_mode"], adaptive_storage_factor=wp["factor"])
+    free_b, _ = torch.cuda.mem_get_info()
+    b = cudapoa.CudaPoaBatch(wp["reads"], wp["max_seq"], int(free_b * 0.45), config=cfg)
+    ours_ms = None
+    for _ in range(2):
+        b.reset()
+        b.add_poa_groups_flat(win_nseq, seq_len, data)
+        t0 = time.perf_counter()
+        b.generate_poa()
+        c, cov, lens, st = b.get_consensus_arrays()
+        ours_ms = (time.perf_counter() - t0) * 1e3
+    ours = [bytes(c[i, :lens[i]]).decode() for i in range(n_windows)]
+    b.close()
+    same = ours == r["consensus"] and list(st) == list(r["status"]) and all(
+        (cov[i, :lens[i]] == r["coverage"][i]).all() for i in range(n_windows))
+    return {"engine": "unmodified cudapoa kernels (oracle/_ref/libgwref.so, sm_100a), generate_poa + get_consensus, host buffers",
+            "windows": n_windows, "value": n_windows / (best / 1e3), "unit": "windows/s", "this_engine_same_call": n_windows / (ours_ms / 1e3),
+            "identical_outputs": bool(same)}
+
+
 def run_reference_arm(args, wp, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (3rdparty/spoa, unmodified, oracle/_ref) on
-    the box's host cores. Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (3rdparty/spoa, unmodified, oracle/_ref) on the box's
+    host cores. Rank 0 only."""
     if rank != 0:
         return
     import ref_lib
@@ -157,31 +252,248 @@ def run_reference_arm(args, wp, rank, world):
         return
     cores = os.cpu_count() or 1
     long_reads = wp["backbone"] >= 5000
-    # bounded sample per step: one window per host thread; long-read windows are cut to their first 3 reads (see spoa_sample)
-    per_step = max(1, min(cores, 256)) if long_reads else max(8, 8 * cores)
-    sample_reads = 3 if long_reads else None
-    times, cells, wps = [], 0.0, []
-    for it in range(args.warmup + args.steps):
-        r = spoa_sample(wp, per_step, 1000 + it * per_step, threads=cores, reads=sample_reads)
-        if it >= args.warmup:
-            times.append(r["seconds"])
-            cells += r["cells"]
-            wps.append(r["windows_per_s"])
-    total = sum(times)
-    value = float(np.mean(wps))
+    if long_reads:
+        value, info = spoa_full_window_stream(wp, args.steps, args.warmup)
+        step_ms = 1e3 * float(np.mean(info["step_seconds"]))
+        full = info["positions_measured"] == info["positions"]
+        sample = ("full %d-read windows, one in progress per host thread (%d threads), %d reads fused per step; %d of %d read positions "
+                  "timed in the %d timed steps%s; value = threads / sum of per-position seconds; spoa DP cells/s %.3e"
+                  % (wp["reads"], info["threads"], info["reads_per_step"], info["positions_measured"], info["positions"], args.steps,
+                     "" if full else " (the others by a straight-line fit)", info["spoa_dp_cells_per_s"]))
+        per_step = info["threads"]
+        extra = {"full_window_stream": {k: v for k, v in info.items() if k != "step_seconds"}, "same_config": bool(full)}
+    else:
+        per_step = max(8, 8 * cores)
+        times, cells, wps = [], 0.0, []
+        for it in range(args.warmup + args.steps):
+            r = spoa_sample(wp, per_step, 1000 + it * per_step, threads=cores)
+            if it >= args.warmup:
+                times.append(r["seconds"])
+                cells += r["cells"]
+                wps.append(r["windows_per_s"])
+        value = float(np.mean(wps))
+        step_ms = 1e3 * sum(times) / max(len(times), 1)
+        sample = "%d full windows per step x %d steps, spoa DP cells/s %.3e" % (per_step, len(times), cells / max(sum(times), 1e-9))
+        extra = {"same_config": True}
     line = {
         "impl": "reference", "metric": "poa_consensus_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int16 (spoa AVX2 SIMD)", "data": "synthetic",
-        "config": {"workload": wp["name"], "windows_per_step": per_step, "engine": "3rdparty/spoa kNW linear gaps, full DP, all host threads"},
-        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "reference",
-                         "sample": "%d windows per step x %d steps, %s, spoa DP cells/s %.3e" % (
-                             per_step, len(times), ("first %d of %d reads per window, windows/s extrapolated by spoa DP cells" % (sample_reads, wp["reads"]))
-                             if sample_reads else "full windows", cells / total)},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16 (spoa AVX2 SIMD)", "data": "synthetic",
+        "config": {"workload": wp["name"], "windows_in_progress_per_step": per_step, "engine": "3rdparty/spoa kNW linear gaps, full DP, all host threads"},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line.update(extra)
+    if not args.no_extras:
+        try:
+            line["gpu_reference"] = gpu_reference_leg(wp, 148 if long_reads else 1024)
+        except Exception as e:  # pragma: no cover
+            line["gpu_reference"] = {"unavailable": "failed: %r" % (e,)}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ------------------------------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX) if self.dist is not None else x
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM) if self.dist is not None else x
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def window_groups(win_nseq, seq_len, data):
+    """Per-window ctypes argument arrays for the drop-in add_poa_group entry (pointers into `data`, built once)."""
+    base = data.ctypes.data
+    groups, off, si = [], 0, 0
+    for ns in win_nseq:
+        ns = int(ns)
+        ptrs = (C.c_char_p * ns)()
+        lens = (C.c_int32 * ns)()
+        for k in range(ns):
+            ptrs[k] = C.cast(base + off, C.c_char_p)
+            lens[k] = int(seq_len[si + k])
+            off += int(seq_len[si + k])
+        si += ns
+        groups.append((ns, ptrs, lens))
+    return groups
+
+
+def poa_leg(D, wp, steps, warmup, msa=False, n_windows=0, sample_clocks=False, mem_fraction=0.95):
+    """One POA workload on every rank: device-resident `value`, API-shaped `e2e`, roofline numbers."""
+    import torch
+    from genomeworks_b200 import _lib, cudapoa, synth
+    L = _lib.lib()
+    cfg = cudapoa.make_config(wp["max_seq"], wp["reads"], wp["band"], wp["band_mode"], adaptive_storage_factor=wp["factor"])
+    stream = torch.cuda.Stream()
+    free_b, _ = torch.cuda.mem_get_info()
+    batch = cudapoa.CudaPoaBatch(wp["reads"], wp["max_seq"], int(free_b * mem_fraction), output_type="msa" if msa else "consensus", config=cfg,
+                                 device_id=D.local_rank, stream=stream)
+    n_win = n_windows or wp["windows"] or min(batch.max_poas, max(batch.resident_windows, 1))
+    n_win = min(n_win, batch.max_poas)
+    win_nseq, seq_len, data = synth.poa_windows(n_win, wp["backbone"], wp["reads"], wp["mut"], wp["ins"], wp["dele"],
+                                                seed0=1000 + D.rank * n_win, max_read_len=wp["max_seq"])
+    # ---- device-resident timing
+    rc, added = batch.add_poa_groups_flat(win_nseq, seq_len, data)
+    assert rc == 0 and added == n_win, (rc, added, n_win)
+    batch.upload()
+    batch.sync()
+    for _ in range(warmup):
+        batch.launch()
+        batch.sync()
+    D.barrier()
+    sampler = ClockSampler(D.local_rank) if (sample_clocks and D.rank == 0) else None
+    if sampler:
+        sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    l0 = L.gwb200_kernel_launch_count()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            batch.launch()
+        ev1.record(stream)
+    stream.synchronize()
+    D.barrier()
+    timed_launches = L.gwb200_kernel_launch_count() - l0
+    dev_ms = D.max(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None
+    cells = batch.last_cells()
+    if msa:
+        _, st = batch.get_msa()
+        st = np.asarray(st)
+        lens = None
+    else:
+        c, cov, lens, st = batch.get_consensus_arrays()
+    n_ok = int((st == 0).sum())
+    total_windows = D.sum(float(n_win))
+    value = total_windows * steps / (dev_ms / 1e3)
+
+    # ---- end to end through the drop-in API: one add_poa_group per window, host buffers, every step
+    groups = window_groups(win_nseq, seq_len, data)
+    add_group = L.gwb200_poa_batch_add_group
+    handle = batch._h
+
+    def e2e_step():
+        batch.reset()
+        for ns, ptrs, lns in groups:
+            rc = add_group(handle, C.c_int32(ns), ptrs, None, lns, None, None)
+            assert rc == 0, rc
+        batch.generate_poa()
+        return batch.get_msa() if msa else batch.get_consensus_arrays()
+
+    for _ in range(max(1, min(warmup, 2))):
+        e2e_step()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = D.max(time.perf_counter() - t0)
+    D.barrier()
+    if not msa:
+        assert (out[2] == lens).all() and (out[3] == st).all()
+    e2e_value = total_windows * steps / e2e_s
+    h2d = int(((seq_len + 3) // 4 * 4).sum()) + 24 * n_win + 4 * len(seq_len)
+    if msa:
+        d2h = n_win * cfg.max_sequences_per_poa * cfg.max_consensus_size + n_win * 20
+    else:
+        d2h = n_win * cfg.max_consensus_size * 3 + n_win * 20
+    sb = batch.score_bytes
+    res = dict(value=value, e2e=e2e_value, dev_ms=dev_ms, k_ms=dev_ms / steps, cells=cells, score_bytes=sb, n_win=n_win, n_ok=n_ok,
+               total_windows=total_windows, h2d=h2d, d2h=d2h, timed_launches=int(timed_launches), clocks=clocks,
+               max_poas=batch.max_poas, resident=batch.resident_windows, status=st, lens=lens)
+    batch.close()
+    del batch
+    torch.cuda.empty_cache()
+    return res
+
+
+def aligner_leg(D, wp, steps, warmup, sample_clocks=False):
+    import torch
+    from genomeworks_b200 import _lib, cudaaligner, synth
+    L = _lib.lib()
+    n = wp["windows"]
+    ql, qd, tl, td = synth.aligner_pairs(n, wp["genome"], seed=1 + D.rank)
+    qb, tb = bytes(qd), bytes(td)
+    pairs, qo, to = [], 0, 0
+    for i in range(n):
+        pairs.append((qb[qo:qo + ql[i]], tb[to:to + tl[i]]))
+        qo += int(ql[i])
+        to += int(tl[i])
+    stream = torch.cuda.Stream()
+    al = cudaaligner.FixedBandAligner(wp["max_bw"], stream=stream, device_id=D.local_rank)
+
+    def step():
+        for q, t in pairs:
+            al.add_alignment(q, t)
+        al.align_all()
+        al.sync_alignments(want_strings=False)
+
+    for _ in range(warmup):
+        step()
+    D.barrier()
+    sampler = ClockSampler(D.local_rank) if (sample_clocks and D.rank == 0) else None
+    if sampler:
+        sampler.start()
+    kms, t0 = 0.0, time.perf_counter()
+    l0 = L.gwb200_kernel_launch_count()
+    for _ in range(steps):
+        step()
+        kms += al.last_kernel_ms()
+    torch.cuda.synchronize()
+    wall = D.max(time.perf_counter() - t0)
+    kms = D.max(kms)
+    D.barrier()
+    clocks = sampler.stop() if sampler else None
+    timed_launches = L.gwb200_kernel_launch_count() - l0
+    cells = al.last_cells()
+    res = al.get_alignments()
+    total = D.sum(float(n))
+    out = dict(value=total * steps / (kms / 1e3), e2e=total * steps / wall, k_ms=kms / steps, cells=cells, n=n, total=total,
+               n_ok=sum(1 for r in res if r.status == 0), n_opt=sum(1 for r in res if r.is_optimal), timed_launches=int(timed_launches),
+               clocks=clocks, h2d=int(ql.sum() + tl.sum()) + 20 * n, d2h=int(sum(len(r.actions) for r in res)) * 5 + 8 * n)
+    al.close()
+    return out
+
+
+def roofline_obj(key, kernel, cells, bytes_per_cell, k_ms, units):
+    peak, peak_src = measured_peaks()
+    achieved = cells * bytes_per_cell / (k_ms / 1e3) / 1e9
+    tr = ncu_traffic(key)
+    traffic = tr["dram_bytes_per_unit"] * units if tr else None
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": (tr or {}).get("source"), "algorithmic_bytes": cells * bytes_per_cell, "peak_source": peak_src, "kernel": kernel,
+            "algorithmic_bytes_per_cell": bytes_per_cell, "kernel_ms_per_launch": k_ms}
 
 
 def main():
@@ -191,192 +503,136 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
-    ap.add_argument("--windows", type=int, default=0, help="windows (or pairs) per GPU per step")
+    ap.add_argument("--windows", type=int, default=0, help="windows (or pairs) per GPU per step (default: what the batch holds)")
     ap.add_argument("--factor", type=float, default=0.0, help="override adaptive_storage_factor of the workload (C3 default 3.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3-MSA / C2 / C4 legs (and gpu_reference in the reference arm)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wp = workload_params(args.workload, args.windows)
+    if args.factor > 0 and wp["kind"] == "poa":
+        wp["factor"] = args.factor
+        wp["name"] = wp["name"].replace("adaptive_storage_factor 3.0", "adaptive_storage_factor %g" % args.factor)
 
     if args.impl == "reference":
         run_reference_arm(args, wp, rank, world)
         return
 
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    D = Dist(rank, world, local_rank)
     from genomeworks_b200 import _lib
     L = _lib.lib()
+    launches0 = L.gwb200_kernel_launch_count()
+    warm = max(args.warmup, 3)
+    xsteps = max(2, min(args.steps, 3))  # the extra legs are short
+
     if wp["kind"] == "aligner":
-        from bench_aligner import run_aligner_bench
-        run_aligner_bench(args, wp, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks)
-        if world > 1:
-            dist.destroy_process_group()
+        r = aligner_leg(D, wp, args.steps, warm, sample_clocks=True)
+        if rank == 0:
+            line = {
+                "metric": "cudaaligner_pairs_per_s", "value": r["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": r["k_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 bit-vectors + int32 scores", "data": "synthetic",
+                "config": {"workload": wp["name"], "pairs_per_gpu_per_step": r["n"], "max_bandwidth": wp["max_bw"],
+                           "l2": "band matrices written per step (%.2f GB) exceed the 126 MB L2" % (r["cells"] * 0.375 / 1e9),
+                           "pairs_ok_last_step": r["n_ok"], "pairs_optimal_last_step": r["n_opt"]},
+                "dp_cells_per_step_per_gpu": r["cells"], "dp_cells_per_s": r["cells"] * world / (r["k_ms"] / 1e3),
+                "roofline": roofline_obj("c4", "myers_banded_kernel", r["cells"], 0.375, r["k_ms"], r["n"]),
+                "e2e": {"value": r["e2e"], "unit": "pairs/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                "gpu_launches": r["timed_launches"], "gpu_launches_total": int(L.gwb200_kernel_launch_count() - launches0), "clocks": r["clocks"],
+                "cpu_baseline": {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference",
+                                 "sample": "no CPU implementation of this path is named by the reference (SURVEY.md 8d)"},
+            }
+            print(json.dumps(line))
+        D.close()
         return
 
-    from genomeworks_b200 import cudapoa, synth
-    if args.factor > 0:
-        wp["factor"] = args.factor
-        wp["name"] = wp["name"].replace("adaptive_storage_factor 3.0", "adaptive_storage_factor %g" % args.factor)
-    cfg = cudapoa.make_config(wp["max_seq"], wp["reads"], wp["band"], wp["band_mode"], adaptive_storage_factor=wp["factor"])
-    stream = torch.cuda.Stream()
-    free_b, _ = torch.cuda.mem_get_info()
-    batch = cudapoa.CudaPoaBatch(wp["reads"], wp["max_seq"], int(free_b * 0.92), config=cfg, device_id=local_rank, stream=stream)
-    n_win = args.windows or wp["windows"]
-    if args.workload == "c3" and not args.windows:
-        # one full batch per GPU: as many windows as the batch holds, rounded to a multiple of the SM count
-        # and capped at what the device keeps resident at once (one wave)
-        n_win = min(batch.max_poas, max(batch.resident_windows, 148))
-        n_win = n_win // 148 * 148 if n_win >= 148 else n_win
-    if batch.max_poas < n_win:
-        raise SystemExit("batch capacity %d < requested windows %d" % (batch.max_poas, n_win))
-    # every rank owns its own windows (seeds disjoint across ranks): weak scaling, no data-path collective
-    win_nseq, seq_len, data = synth.poa_windows(n_win, wp["backbone"], wp["reads"], wp["mut"], wp["ins"], wp["dele"],
-                                                seed0=1000 + rank * n_win, max_read_len=wp["max_seq"])
-
-    launches0 = L.gwb200_kernel_launch_count()
-
-    # ---------------- device-resident timing (`value`) ----------------
-    rc, added = batch.add_poa_groups_flat(win_nseq, seq_len, data)
-    assert rc == 0 and added == n_win
-    batch.upload()
-    batch.sync()
-    for _ in range(args.warmup):
-        batch.launch()
-        batch.sync()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    launches_before_timed = L.gwb200_kernel_launch_count()
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(args.steps):
-            batch.launch()
-        ev1.record(stream)
-    stream.synchronize()
-    barrier()
-    timed_launches = L.gwb200_kernel_launch_count() - launches_before_timed
-    dev_ms = ev0.elapsed_time(ev1)
-    dev_ms = max_over_ranks(dev_ms)
-    clocks = sampler.stop() if rank == 0 else None
-    cells = batch.last_cells()
-    last_kernel_ms = batch.last_kernel_ms()
-    c, cov, lens, st = batch.get_consensus_arrays()
-    n_ok = int((st == 0).sum())
-    total_windows = sum_over_ranks(float(n_win))
-    value = total_windows * args.steps / (dev_ms / 1e3)
-
-    # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
-    # sequences (padded to 4 B per read) + window descriptors + read lengths; base weights are unit weights here and are
-    # set on the device (no host traffic)
-    h2d = int(((seq_len + 3) // 4 * 4).sum()) + 24 * n_win + 4 * len(seq_len)
-    d2h = n_win * cfg.max_consensus_size * 3 + n_win * 20
-    for _ in range(max(1, min(args.warmup, 2))):
-        batch.reset()
-        batch.add_poa_groups_flat(win_nseq, seq_len, data)
-        batch.generate_poa()
-        batch.get_consensus_arrays()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        batch.reset()
-        batch.add_poa_groups_flat(win_nseq, seq_len, data)
-        batch.generate_poa()
-        c2, cov2, lens2, st2 = batch.get_consensus_arrays()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = total_windows * args.steps / e2e_s
-    assert (lens2 == lens).all() and (st2 == st).all()
+    r = poa_leg(D, wp, args.steps, warm, n_windows=args.windows, sample_clocks=True)
+    extras = {}
+    if not args.no_extras and args.workload == "c3":
+        try:
+            m = poa_leg(D, wp, xsteps, 3, msa=True)
+            extras["c3_msa"] = {"metric": "poa_msa_windows_per_s", "value": m["value"], "e2e": m["e2e"], "unit": "windows/s",
+                                "windows_per_gpu_per_step": m["n_win"], "windows_ok": m["n_ok"], "ms_per_step": m["k_ms"],
+                                "roofline_frac": roofline_obj("c3_msa", "poa_window_kernel_v3", m["cells"], m["score_bytes"], m["k_ms"], m["n_win"])["frac"]}
+        except Exception as e:  # pragma: no cover
+            extras["c3_msa"] = {"failed": repr(e)}
+        try:
+            w2 = workload_params("c2")
+            c2 = poa_leg(D, w2, xsteps, 3, mem_fraction=0.3)
+            extras["c2"] = {"metric": "poa_consensus_windows_per_s", "workload": w2["name"], "value": c2["value"], "e2e": c2["e2e"], "unit": "windows/s",
+                            "windows_per_gpu_per_step": c2["n_win"], "windows_ok": c2["n_ok"], "ms_per_step": c2["k_ms"],
+                            "roofline_frac": roofline_obj("c2", "poa_window_kernel_v3", c2["cells"], c2["score_bytes"], c2["k_ms"], c2["n_win"])["frac"]}
+            c2b = poa_leg(D, w2, xsteps, 3, n_windows=16 * 1024, mem_fraction=0.3)
+            extras["c2_full_machine"] = {"workload": w2["name"] + " (16384 windows per step: the 1024-window BASELINE batch is 0.43 of one residency)",
+                                         "value": c2b["value"], "e2e": c2b["e2e"], "unit": "windows/s", "windows_per_gpu_per_step": c2b["n_win"],
+                                         "roofline_frac": roofline_obj("c2", "poa_window_kernel_v3", c2b["cells"], c2b["score_bytes"], c2b["k_ms"], c2b["n_win"])["frac"]}
+        except Exception as e:  # pragma: no cover
+            extras["c2"] = {"failed": repr(e)}
+        try:
+            w4 = workload_params("c4")
+            a = aligner_leg(D, w4, max(xsteps, 5), 3)
+            extras["c4"] = {"metric": "cudaaligner_pairs_per_s", "workload": w4["name"], "value": a["value"], "e2e": a["e2e"], "unit": "pairs/s",
+                            "pairs_per_gpu_per_step": a["n"], "pairs_ok": a["n_ok"], "pairs_optimal": a["n_opt"], "ms_per_step": a["k_ms"],
+                            "roofline_frac": roofline_obj("c4", "myers_banded_kernel", a["cells"], 0.375, a["k_ms"], a["n"])["frac"]}
+        except Exception as e:  # pragma: no cover
+            extras["c4"] = {"failed": repr(e)}
 
     # result gather over NCCL (outside the timed regions): per-window status + consensus length to rank 0
+    n_ok = r["n_ok"]
     if world > 1:
-        mine = torch.from_numpy(np.stack([st.astype(np.int32), lens.astype(np.int32)], 1)).cuda()
+        mine = torch.from_numpy(np.stack([r["status"].astype(np.int32), r["lens"].astype(np.int32)], 1)).cuda()
         gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)
+        D.dist.gather(mine, gathered, dst=0)
         if rank == 0:
             n_ok = int(sum(int((g[:, 0] == 0).sum().item()) for g in gathered))
 
-    launches = L.gwb200_kernel_launch_count() - launches0
-
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        sb = batch.score_bytes
-        k_ms = dev_ms / args.steps
-        achieved = cells * sb / (k_ms / 1e3) / 1e9
+        sb = r["score_bytes"]
         line = {
-            "metric": "poa_consensus_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "poa_consensus_windows_per_s", "value": r["value"], "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": r["k_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32" if sb == 4 else "int16", "data": "synthetic",
-            "config": {"workload": wp["name"], "windows_per_gpu_per_step": n_win, "reads_per_window": wp["reads"],
+            "config": {"workload": wp["name"], "windows_per_gpu_per_step": r["n_win"], "reads_per_window": wp["reads"],
                        "band_mode": wp["band_mode"], "band_width": wp["band"], "scores": "gap -8 mismatch -6 match 8",
-                       "parallelism": "windows sharded over %d GPU(s), one Batch per rank" % world,
-                       "l2": "score matrices written per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (cells * sb / 1e9),
+                       "batch_capacity_windows": r["max_poas"], "resident_windows_per_gpu": r["resident"],
+                       "parallelism": "windows sharded over %d GPU(s), one Batch per rank, persistent grid (one warp per window)" % world,
+                       "l2": "score matrices written per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (r["cells"] * sb / 1e9),
                        "windows_ok_last_step": n_ok},
-            "dp_cells_per_step_per_gpu": cells, "dp_cells_per_s": cells * world / (k_ms / 1e3),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_WINDOW.get(args.workload, 0) * n_win or None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per window from the ncu --set full captures in "
-                                           "profiles/r01_poa_v2_{c3,c2}_ncu.md (16 / 1024 windows), scaled to this launch's window count",
-                         "algorithmic_bytes": cells * sb,
-                         "peak_source": peak_src, "kernel": "poa_window_kernel_v2", "algorithmic_bytes_per_cell": sb,
-                         "kernel_ms_per_launch": k_ms},
-            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(timed_launches), "gpu_launches_total": int(launches), "clocks": clocks,
+            "dp_cells_per_step_per_gpu": r["cells"], "dp_cells_per_s": r["cells"] * world / (r["k_ms"] / 1e3),
+            "roofline": roofline_obj(wp["key"], "poa_window_kernel_v3", r["cells"], sb, r["k_ms"], r["n_win"]),
+            "e2e": {"value": r["e2e"], "unit": "windows/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "api": "Batch::add_poa_group once per window + generate_poa + get_consensus (host buffers)"},
+            "gpu_launches": r["timed_launches"], "gpu_launches_total": int(L.gwb200_kernel_launch_count() - launches0), "clocks": r["clocks"],
         }
-        if not args.no_cpu_baseline:
+        if extras:
+            line["extra"] = extras
+        if not args.no_cpu_baseline and world >= 1:
             try:
                 import ref_lib
                 if ref_lib.have_spoa():
                     cores = os.cpu_count() or 1
                     long_reads = wp["backbone"] >= 5000
                     ns = max(1, min(cores, 256)) if long_reads else 8 * cores
-                    r = spoa_sample(wp, ns, 1000, threads=cores, reads=3 if long_reads else None)
-                    line["cpu_baseline"] = {"value": r["windows_per_s"], "unit": "windows/s", "cores": cores, "kind": "reference",
+                    s = spoa_sample(wp, ns, 1000, threads=cores, reads=3 if long_reads else None)
+                    line["cpu_baseline"] = {"value": s["windows_per_s"], "unit": "windows/s", "cores": cores, "kind": "reference",
                                             "sample": "%d windows of the same workload%s, unmodified 3rdparty/spoa (AVX2), %.1f s, %.3e spoa DP cells/s"
-                                                      % (ns, (" cut to their first %d reads, windows/s extrapolated by spoa DP-cell count (x%.4f)"
-                                                              % (r["reads_used"], r["scale"])) if long_reads else "", r["seconds"],
-                                                         r["cells"] / r["seconds"])}
+                                                      % (ns, (" cut to their first %d reads, windows/s extrapolated by spoa DP-cell count (x%.4f); "
+                                                              "full windows are timed by --impl reference" % (s["reads_used"], s["scale"]))
+                                                         if long_reads else "", s["seconds"], s["cells"] / s["seconds"])}
                 else:
                     line["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": 0, "kind": "reference",
                                             "sample": "oracle/_ref/libspoa_ref.so not built"}
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -280,3 +280,49 @@ def test_c3_shape_storage_factor_status_parity_vs_reference():
             assert set(ours["status"]) == {cudapoa.exceeded_adaptive_banded_matrix_size}
         else:
             assert (ours["status"] == 0).all()
+
+
+def test_c3_full_shape_msa_vs_reference():
+    """BASELINE config 3 as it is stated: long-read MSA, 10 kb windows x 32 reads, adaptive band, OutputType::msa -- rows and
+    statuses bit-exact against the unmodified reference kernels (cudapoa_generate_msa.cuh:127-227 keeps 98 MB/window of per-edge
+    read lists; this engine derives the rows from per-read node paths). Also the consensus of the same windows."""
+    if not ref_lib.have_gwref():
+        pytest.skip("oracle/_ref/libgwref.so not built")
+    from genomeworks_b200 import cudapoa, synth
+    n = 6
+    win_nseq, seq_len, data = synth.poa_windows(n, 10000, 32, 200, 100, 100, seed0=1000, max_read_len=10240)
+    cfg = cudapoa.make_config(10240, 32, 256, "adaptive_band", adaptive_storage_factor=3.0)
+    ours = run_ours(win_nseq, seq_len, data, cfg, msa=True, mem=12 << 30)
+    ref = ref_lib.ref_poa_run(win_nseq, seq_len, data, 10240, 32, 256, 2, adaptive_storage_factor=3.0, msa=True, mem_fraction=0.4,
+                              max_windows_per_batch=n)
+    assert list(ours["status"]) == list(ref["status"]) and (ours["status"] == 0).all()
+    windows = synth.split_windows(win_nseq, seq_len, data)
+    for w in range(n):
+        assert len(ours["msa"][w]) == 32
+        assert ours["msa"][w] == ref["msa"][w], "MSA rows of window %d differ" % w
+        for row, rd in zip(ours["msa"][w], windows[w]):
+            assert row.replace("-", "") == rd
+    ours_c = run_ours(win_nseq, seq_len, data, cfg, mem=12 << 30)
+    ref_c = ref_lib.ref_poa_run(win_nseq, seq_len, data, 10240, 32, 256, 2, adaptive_storage_factor=3.0, mem_fraction=0.4, max_windows_per_batch=n)
+    assert_same_consensus(ours_c, ref_c, "reference")
+
+
+def test_empty_group_stays_in_the_batch_without_touching_other_windows():
+    """A group whose reads are all rejected returns empty_poa_group but still occupies a slot (cudapoa_batch.cuh:139-148); the
+    kernels must not read a read length for it (it would be the next window's). Its status is empty_poa_group, the windows
+    around it are unaffected."""
+    from genomeworks_b200 import cudapoa
+    cfg = cudapoa.make_config(1024, 10, 256, "static_band")
+    good = ["ACGTTGCAAGCTTGCATGCA" * 10, "ACGTTGCAAGCTAGCATGCA" * 10, "ACGTTGCAAGCTTGCATGCA" * 10]
+    for kernel_env in (None,):
+        b = cudapoa.CudaPoaBatch(10, 1024, 1 << 30, config=cfg)
+        assert b.add_poa_group(good)[0] == cudapoa.success
+        assert b.add_poa_group(["A" * 1025])[0] == cudapoa.empty_poa_group
+        assert b.add_poa_group(good)[0] == cudapoa.success
+        assert b.add_poa_group(["C" * 2000, "G" * 1500])[0] == cudapoa.empty_poa_group
+        assert b.total_poas == 4
+        b.generate_poa()
+        cons, cov, st = b.get_consensus()
+        assert st == [0, cudapoa.empty_poa_group, 0, cudapoa.empty_poa_group], st
+        assert cons[0] == good[0] and cons[2] == good[0] and cons[1] == "" and cons[3] == ""
+        b.close()

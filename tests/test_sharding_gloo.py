@@ -59,3 +59,49 @@ def test_gather_restores_input_order_world2():
     for p in procs:
         p.join(timeout=60)
     assert ok
+
+
+def _scatter_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from genomeworks_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(5)
+    n = 23
+    nseq = rng.randint(2, 7, size=n).astype(np.int32)
+    lens = rng.randint(20, 90, size=int(nseq.sum())).astype(np.int32)
+    data = rng.randint(65, 85, size=int(lens.sum()) + 1).astype(np.uint8)
+    if rank == 0:
+        idx, ns, sl, sd, n_total = sharding.scatter_windows(nseq, lens, data, dist)
+    else:
+        idx, ns, sl, sd, n_total = sharding.scatter_windows(None, None, None, dist)
+    # every rank checks its shard against the partition computed from the full list (all ranks can build it: same seed)
+    shards = sharding.partition_units(sharding.window_costs(nseq, lens), world)
+    ok = n_total == n and (idx == shards[rank]).all() and (ns == nseq[shards[rank]]).all()
+    r_end = np.cumsum(nseq)
+    r_start = r_end - nseq
+    b = np.concatenate([[0], np.cumsum(lens.astype(np.int64))])
+    exp_len = np.concatenate([lens[r_start[w]:r_end[w]] for w in shards[rank]])
+    exp_dat = np.concatenate([data[b[r_start[w]]:b[r_end[w]]] for w in shards[rank]])
+    ok = ok and (sl == exp_len).all() and (sd[:-1] == exp_dat).all()
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(float(t.item()) == 1.0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_windows_world2():
+    """Input scatter of a fixed window list from rank 0 (sharding.scatter_windows), gloo, world size 2."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 300)
+    procs = [ctx.Process(target=_scatter_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok
