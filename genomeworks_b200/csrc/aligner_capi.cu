@@ -350,11 +350,12 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     const int32_t n_blocks = static_cast<int32_t>(std::min<int64_t>(static_cast<int64_t>(a->n_sms) * kBlocksPerSM, n));
     const int32_t qpat_el  = 4 * ((a->max_query + 31) / 32) + 4;
     const int64_t ws       = std::max<int64_t>(a->max_matrix, 1);
+    const int64_t ws_pitch = (ws + 3) & ~3ll; // 16-byte aligned workspaces: the backtrace stages them by bulk copies
     bool ok = a->seq_d.ensure(seq_sum + 16) && a->seq_starts_d.ensure(2ll * n + 1) && a->max_bw_d.ensure(n) && a->sched_d.ensure(n) &&
               a->counter_d.ensure(1) && a->path_len_d.ensure(n) && a->offsets_d.ensure(n + 1) && a->metadata_d.ensure(n) &&
               a->slot_actions_d.ensure(seq_sum + 16) && a->slot_runs_d.ensure(seq_sum + 16) && a->actions_d.ensure(seq_sum + 16) &&
-              a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(ws * n_blocks) && a->mv_d.ensure(ws * n_blocks) &&
-              a->score_d.ensure(ws * n_blocks) && a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
+              a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(ws_pitch * n_blocks) && a->mv_d.ensure(ws_pitch * n_blocks) &&
+              a->score_d.ensure(ws_pitch * n_blocks) && a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
               a->offsets_h.ensure(n + 1, false) && a->metadata_h.ensure(n, false) && a->cells_h.ensure(1, false);
     if (!ok)
         return set_error(GWB200_E_RUNTIME, "Out of memory.");
@@ -385,6 +386,7 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     P.mv            = a->mv_d.p;
     P.score         = a->score_d.p;
     P.ws_elems      = ws;
+    P.ws_stride     = ws_pitch;
     P.qpat          = a->qpat_d.p;
     P.qpat_elems    = qpat_el;
     P.slot_actions  = a->slot_actions_d.p;

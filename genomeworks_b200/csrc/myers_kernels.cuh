@@ -24,6 +24,7 @@ typedef uint32_t WordType;
 constexpr int32_t kWord       = 32;
 constexpr int32_t kStageCols  = 32;
 constexpr int32_t kStageStride = 33; // words per staged column (+1: lanes that read consecutive columns hit distinct banks)
+constexpr int32_t kQpatSmemWords = 320; // queries of up to 10 240 bases keep their bit patterns in shared memory
 constexpr uint32_t kFull      = 0xffffffffu;
 constexpr int32_t kOutOfBand  = INT32_MAX - 1; // myers_gpu.cu:448
 
@@ -48,6 +49,7 @@ struct DeviceParams
     WordType* mv;
     int32_t* score;
     int64_t ws_elems;            // elements per CTA in pv / mv / score
+    int64_t ws_stride;           // distance between the CTAs' workspaces (ws_elems rounded up to 4 elements: 16-byte aligned)
     WordType* qpat;
     int32_t qpat_elems;          // elements per CTA (>= 4 * ceil(max_query/32))
     // per-alignment result slots: alignment i owns [seq_starts[2i], seq_starts[2i+2])
@@ -59,6 +61,74 @@ struct DeviceParams
 };
 
 __device__ __forceinline__ int32_t ceil_div(int32_t a, int32_t b) { return (a + b - 1) / b; }
+
+// ---- shared-memory / TMA helpers (1-D bulk asynchronous copy completing on an mbarrier)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sdst)),
+                 "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t done = 0, spins = 0;
+    while (!done)
+    {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+        if (++spins > (1u << 22))
+            __trap(); // a copy that never completes is a bug: fail loudly instead of hanging the device
+    }
+}
+
+// Query bit patterns of the fast path: [4][n_words + 1] words in shared memory (one zero word of padding per character, so the
+// unaligned 32-bit window of the diagonal phase is always two loads and one funnel shift), or the global [4][n_words] array.
+struct QPat
+{
+    uint32_t sbase;        // shared address, 0 = use the global array
+    const WordType* gbase;
+    int32_t n_words;
+    // get_query_pattern, myers_gpu.cu:210-241
+    __device__ __forceinline__ WordType get(int32_t idx, int32_t query_begin_offset, char x) const
+    {
+        const int32_t char_idx = (x >> 1) & 0x3;
+        const int32_t w        = idx + (query_begin_offset >> 5);
+        const int32_t shift    = query_begin_offset & 31;
+        if (sbase != 0)
+        {
+            const uint32_t a  = sbase + static_cast<uint32_t>(char_idx * (n_words + 1) + w) * 4u;
+            const uint32_t lo = lds_u32(a);
+            const uint32_t hi = lds_u32(a + 4u);
+            return __funnelshift_r(lo, hi, shift);
+        }
+        const WordType* col = gbase + char_idx * n_words;
+        WordType r          = col[w];
+        if (shift != 0)
+        {
+            r >>= shift;
+            if (w + 1 < n_words)
+                r |= col[w + 1] << (kWord - shift);
+        }
+        return r;
+    }
+};
 
 // column-major matrix view, data[i + n_rows * j] (cf. batched_device_matrices.cuh:61-76)
 template <typename T>
@@ -138,32 +208,54 @@ struct BandRegs
 };
 
 __device__ __forceinline__ void horizontal_fast(uint32_t mask, int32_t lane, BandRegs& R, const View<WordType>& pvm, const View<WordType>& mvm,
-                                                const View<int32_t>& scm, const WordType* qpat, int32_t n_words_query, const char* target,
-                                                int32_t t_begin, int32_t t_end, int32_t width, int32_t n_words, int32_t pattern_idx_offset)
+                                                const View<int32_t>& scm, const QPat& Q, const char* target, int32_t t_begin, int32_t t_end,
+                                                int32_t width, int32_t n_words, int32_t pattern_idx_offset)
 {
+    if (t_begin >= t_end)
+        return;
     const WordType hb = WordType(1) << (lane == (n_words - 1) ? width - (n_words - 1) * kWord - 1 : kWord - 1);
+    // the pattern of column t + 1 is fetched while column t is computed (neither load depends on the recurrence)
+    WordType eq_next  = Q.get(lane, pattern_idx_offset, __ldg(target + t_begin - 1));
+    WordType* pvp     = &pvm(lane, t_begin);
+    WordType* mvp     = &mvm(lane, t_begin);
+    int32_t* scp      = &scm(lane, t_begin);
+    const int32_t rows = pvm.rows;
     for (int32_t t = t_begin; t < t_end; ++t)
     {
-        const char tc     = target[t - 1];
-        const WordType eq = query_pattern(qpat, n_words_query, lane, pattern_idx_offset, tc);
-        const int2 c      = advance_block(mask, lane, hb, eq, R.pv, R.mv, lane == 0 ? 1 : 0);
+        const WordType eq = eq_next;
+        if (t + 1 < t_end)
+            eq_next = Q.get(lane, pattern_idx_offset, __ldg(target + t));
+        const int2 c = advance_block(mask, lane, hb, eq, R.pv, R.mv, lane == 0 ? 1 : 0);
         R.sc += c.x;
-        pvm(lane, t) = R.pv;
-        mvm(lane, t) = R.mv;
-        scm(lane, t) = R.sc;
+        *pvp = R.pv;
+        *mvp = R.mv;
+        *scp = R.sc;
+        pvp += rows;
+        mvp += rows;
+        scp += rows;
     }
 }
 
 __device__ __forceinline__ void diagonal_fast(uint32_t mask, int32_t lane, BandRegs& R, const View<WordType>& pvm, const View<WordType>& mvm,
-                                              const View<int32_t>& scm, const WordType* qpat, int32_t n_words_query, const char* target,
-                                              int32_t t_begin, int32_t t_end, int32_t band_width, int32_t n_words_band)
+                                              const View<int32_t>& scm, const QPat& Q, const char* target, int32_t t_begin, int32_t t_end,
+                                              int32_t band_width, int32_t n_words_band)
 {
+    if (t_begin >= t_end)
+        return;
     const bool last      = lane == n_words_band - 1;
     const WordType drb   = WordType(1) << (last ? band_width - (n_words_band - 1) * kWord - 2 : kWord - 2);
     const WordType ddb   = drb << 1;
     const bool has_above = (mask >> lane) > 1u;
+    WordType eq_next     = Q.get(lane, 1, __ldg(target + t_begin - 1));
+    WordType* pvp        = &pvm(lane, t_begin);
+    WordType* mvp        = &mvm(lane, t_begin);
+    int32_t* scp         = &scm(lane, t_begin);
+    const int32_t rows   = pvm.rows;
     for (int32_t t = t_begin; t < t_end; ++t)
     {
+        const WordType eq = eq_next;
+        if (t + 1 < t_end)
+            eq_next = Q.get(lane, t - t_begin + 2, __ldg(target + t));
         // previous column shifted down by one row: warp_rightshift_sync on pv and mv (myers_gpu.cu:91-102, 705-706)
         const uint32_t lows = (R.pv & 1u) | ((R.mv & 1u) << 1);
         const uint32_t in   = __shfl_down_sync(mask, lows, 1);
@@ -174,8 +266,6 @@ __device__ __forceinline__ void diagonal_fast(uint32_t mask, int32_t lane, BandR
             pv |= (in & 1u) << 31;
             mv |= (in >> 1) << 31;
         }
-        const char tc     = target[t - 1];
-        const WordType eq = query_pattern(qpat, n_words_query, lane, t - t_begin + 1, tc);
         if (last)
         {
             // bits without a left neighbour: assume the worst case +1 (:721-726)
@@ -187,9 +277,12 @@ __device__ __forceinline__ void diagonal_fast(uint32_t mask, int32_t lane, BandR
         R.sc += c.x + delta_down;
         R.pv = pv;
         R.mv = mv;
-        pvm(lane, t) = pv;
-        mvm(lane, t) = mv;
-        scm(lane, t) = R.sc;
+        *pvp = pv;
+        *mvp = mv;
+        *scp = R.sc;
+        pvp += rows;
+        mvp += rows;
+        scp += rows;
     }
 }
 
@@ -288,7 +381,7 @@ __device__ void diagonal_general(int32_t lane, const View<WordType>& pvm, const 
 
 // myers_compute_scores_edit_dist_banded, myers_gpu.cu:753-846
 __device__ void compute_scores_banded(int32_t lane, int32_t& diagonal_begin, int32_t& diagonal_end, const View<WordType>& pvm,
-                                      const View<WordType>& mvm, const View<int32_t>& scm, const WordType* qpat, int32_t n_words_query,
+                                      const View<WordType>& mvm, const View<int32_t>& scm, const QPat& Q, const WordType* qpat, int32_t n_words_query,
                                       const char* target, int32_t target_size, int32_t query_size, int32_t band_width, int32_t n_words_band,
                                       int32_t p)
 {
@@ -319,13 +412,13 @@ __device__ void compute_scores_banded(int32_t lane, int32_t& diagonal_begin, int
             scm(lane, 0) = R.sc;
             if (full_myers)
             {
-                horizontal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, 1, target_size + 1, query_size, n_words_band, 0);
+                horizontal_fast(mask, lane, R, pvm, mvm, scm, Q, target, 1, target_size + 1, query_size, n_words_band, 0);
             }
             else
             {
-                horizontal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, 1, diagonal_begin, band_width, n_words_band, 0);
-                diagonal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, diagonal_begin, diagonal_end, band_width, n_words_band);
-                horizontal_fast(mask, lane, R, pvm, mvm, scm, qpat, n_words_query, target, diagonal_end, target_size + 1, band_width, n_words_band,
+                horizontal_fast(mask, lane, R, pvm, mvm, scm, Q, target, 1, diagonal_begin, band_width, n_words_band, 0);
+                diagonal_fast(mask, lane, R, pvm, mvm, scm, Q, target, diagonal_begin, diagonal_end, band_width, n_words_band);
+                horizontal_fast(mask, lane, R, pvm, mvm, scm, Q, target, diagonal_end, target_size + 1, band_width, n_words_band,
                                 query_size - band_width);
             }
         }
@@ -362,22 +455,48 @@ struct Stage
     View<int32_t> scm;
     int32_t n_words_band;
     int32_t jlo, jhi; // staged columns [jlo, jhi]; jhi < jlo => nothing staged
+    int32_t sstride;  // words per staged column
+    unsigned long long* bar; // mbarrier of the bulk copies and its next wait parity (kept across alignments: the barrier lives with the CTA)
+    uint32_t phase;
     bool use_smem;
     WordType last_entry_mask;
 
     __device__ __forceinline__ void refill(int32_t j, int32_t lane)
     {
-        // make columns [j - kStageCols + 1, j] resident (clamped at 0)
+        // make columns [j - kStageCols + 1, j] resident (clamped at 0). The staged block is one contiguous piece of each
+        // column-major matrix (n_words_band words per column): with a multiple of 4 words per column it is fetched by three
+        // bulk asynchronous copies (TMA) that complete on the CTA's mbarrier, otherwise by coalesced loads of all lanes.
         __syncwarp();
         jhi = j;
         jlo = max(0, j - kStageCols + 1);
-        if (lane < n_words_band)
+        const int32_t n_el = (jhi - jlo + 1) * n_words_band;
+        const int64_t off  = static_cast<int64_t>(jlo) * n_words_band;
+        if ((n_words_band & 3) == 0 && ((reinterpret_cast<uintptr_t>(pvm.data) | reinterpret_cast<uintptr_t>(mvm.data) | reinterpret_cast<uintptr_t>(scm.data)) & 15) == 0)
         {
-            for (int32_t c = 0; c <= jhi - jlo; c++)
+            sstride = n_words_band;
+            if (lane == 0)
             {
-                s_pv[c * kStageStride + lane] = pvm(lane, jlo + c);
-                s_mv[c * kStageStride + lane] = mvm(lane, jlo + c);
-                s_sc[c * kStageStride + lane] = scm(lane, jlo + c);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of the stage vs. the async writes
+                const uint32_t bytes = static_cast<uint32_t>(n_el) * 4u;
+                mbar_arrive_expect_tx(bar, 3u * bytes);
+                bulk_load_g2s(s_pv, pvm.data + off, bytes, bar);
+                bulk_load_g2s(s_mv, mvm.data + off, bytes, bar);
+                bulk_load_g2s(s_sc, scm.data + off, bytes, bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+        else
+        {
+            sstride = kStageStride;
+            for (int32_t e = lane; e < n_el; e += 32)
+            {
+                const int32_t c = e / n_words_band;
+                const int32_t w = e - c * n_words_band;
+                s_pv[c * kStageStride + w] = pvm.data[off + e];
+                s_mv[c * kStageStride + w] = mvm.data[off + e];
+                s_sc[c * kStageStride + w] = scm.data[off + e];
             }
         }
         __syncwarp();
@@ -394,7 +513,7 @@ struct Stage
         WordType p, m;
         if (use_smem)
         {
-            const int32_t o = (j - jlo) * kStageStride + word_idx;
+            const int32_t o = (j - jlo) * sstride + word_idx;
             s = s_sc[o];
             p = s_pv[o];
             m = s_mv[o];
@@ -652,17 +771,26 @@ __device__ __forceinline__ int32_t fetch_task(const DeviceParams& P, int32_t lan
 }
 
 // myers_banded_kernel, myers_gpu.cu:862-1032
-__global__ void __launch_bounds__(32, 16) myers_banded_kernel(const DeviceParams P)
+__global__ void __launch_bounds__(32, 12) myers_banded_kernel(const DeviceParams P)
 {
-    __shared__ WordType s_pv[kStageCols * kStageStride];
-    __shared__ WordType s_mv[kStageCols * kStageStride];
-    __shared__ int32_t s_sc[kStageCols * kStageStride];
+    __shared__ __align__(16) WordType s_pv[kStageCols * kStageStride];
+    __shared__ __align__(16) WordType s_mv[kStageCols * kStageStride];
+    __shared__ __align__(16) int32_t s_sc[kStageCols * kStageStride];
+    __shared__ __align__(16) WordType s_qpat[4 * (kQpatSmemWords + 1)];
+    __shared__ unsigned long long s_bar;
+    uint32_t bar_phase = 0;
+    if (threadIdx.x == 0)
+    {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     const int32_t lane = threadIdx.x;
     WordType* qpat     = P.qpat + static_cast<int64_t>(blockIdx.x) * P.qpat_elems;
-    WordType* pv_ws    = P.pv + static_cast<int64_t>(blockIdx.x) * P.ws_elems;
-    WordType* mv_ws    = P.mv + static_cast<int64_t>(blockIdx.x) * P.ws_elems;
-    int32_t* sc_ws     = P.score + static_cast<int64_t>(blockIdx.x) * P.ws_elems;
+    WordType* pv_ws    = P.pv + static_cast<int64_t>(blockIdx.x) * P.ws_stride;
+    WordType* mv_ws    = P.mv + static_cast<int64_t>(blockIdx.x) * P.ws_stride;
+    int32_t* sc_ws     = P.score + static_cast<int64_t>(blockIdx.x) * P.ws_stride;
     unsigned long long my_cells = 0;
 
     int32_t a = fetch_task(P, lane);
@@ -725,8 +853,21 @@ __global__ void __launch_bounds__(32, 16) myers_banded_kernel(const DeviceParams
             qpat[n_words + idx]     = rC;
             qpat[2 * n_words + idx] = rT;
             qpat[3 * n_words + idx] = rG;
+            if (n_words <= kQpatSmemWords)
+            {
+                s_qpat[idx]                     = rA;
+                s_qpat[(n_words + 1) + idx]     = rC;
+                s_qpat[2 * (n_words + 1) + idx] = rT;
+                s_qpat[3 * (n_words + 1) + idx] = rG;
+            }
         }
+        if (n_words <= kQpatSmemWords && lane < 4)
+            s_qpat[lane * (n_words + 1) + n_words] = 0;
         __syncwarp();
+        QPat Q;
+        Q.sbase   = n_words <= kQpatSmemWords ? smem_addr(s_qpat) : 0u;
+        Q.gbase   = qpat;
+        Q.n_words = n_words;
 
         // Ukkonen band doubling (:955-1002)
         int32_t max_distance_estimate = max(1, abs(target_size - query_size) + min(target_size, query_size) / 20);
@@ -759,7 +900,7 @@ __global__ void __launch_bounds__(32, 16) myers_banded_kernel(const DeviceParams
             mvm.rows     = nwb;
             scm.rows     = nwb;
             my_cells += static_cast<unsigned long long>(band_width) * static_cast<unsigned long long>(target_size);
-            compute_scores_banded(lane, diagonal_begin, diagonal_end, pvm, mvm, scm, qpat, n_words, target, target_size, query_size, band_width,
+            compute_scores_banded(lane, diagonal_begin, diagonal_end, pvm, mvm, scm, Q, qpat, n_words, target, target_size, query_size, band_width,
                                   nwb, p);
             __syncwarp();
             const int32_t cur_edit_distance = nwb > 0 ? scm(nwb - 1, target_size) : target_size;
@@ -786,7 +927,11 @@ __global__ void __launch_bounds__(32, 16) myers_banded_kernel(const DeviceParams
             S.jlo          = 0;
             S.jhi          = -1;
             S.use_smem     = n_words_band <= 32;
+            S.sstride      = kStageStride;
+            S.bar          = &s_bar;
+            S.phase        = bar_phase;
             path_length    = backtrace_banded(lane, S, out_actions, out_runs, diagonal_begin, diagonal_end, abs(band_width), target_size);
+            bar_phase      = S.phase;
         }
         if (lane == 0)
         {

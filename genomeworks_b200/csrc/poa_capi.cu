@@ -224,6 +224,13 @@ int32_t v3_pool_bytes(gwb200_poa_batch* b)
     int smem_sm = 233472;
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, b->device_id);
     int32_t ctas = static_cast<int32_t>(std::min<int64_t>(16, std::max<int64_t>(1, (static_cast<int64_t>(b->max_poas) + sms - 1) / sms)));
+    {
+        // 32-bit scores run their rows as a wavefront (poa_kernels_v4.cuh): 32 rows in flight per window need windows of
+        // 33 x (Wg x 20 + 20) bytes, Wg = 48 slots for the widest adaptive bands -> 6 windows per SM
+        const char* e = std::getenv("GWB200_POA_WAVEFRONT");
+        if (b->score32 && e && std::atoi(e) != 0)
+            ctas = std::min(ctas, 6);
+    }
     if (const char* c = std::getenv("GWB200_POA_CTAS_PER_SM")) // development switch
         ctas = std::max(1, std::min(32, std::atoi(c)));
     if (const char* kb = std::getenv("GWB200_POA_POOL_KB")) // development switch
@@ -800,6 +807,8 @@ static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void
             b->Y.use_bulk   = (e && std::atoi(e) == 0) ? 0 : 1;
             e               = std::getenv("GWB200_POA_TB_TMA");
             b->Y.tb_tma     = (e && std::atoi(e) == 0) ? 0 : 1;
+            e               = std::getenv("GWB200_POA_WAVEFRONT");
+            b->Y.wavefront  = (e && std::atoi(e) != 0) ? 1 : 0; // off by default until it beats dp_rows_v3 (development switch)
         }
     }
     gwb200_poa_batch_reset(b);

@@ -84,6 +84,7 @@ struct V3Extra
     int32_t* work_counter; // next window index (persistent grid), reset by the host before every launch
     int32_t use_bulk;      // 1: rows leave the ring by cp.async.bulk (default); 0: per-lane vector stores (A/B switch)
     int32_t tb_tma;        // 1: traceback tiles by bulk asynchronous copies with prefetch (default); 0: lane loads (A/B switch)
+    int32_t wavefront;     // 1: 32-bit score rows as a skewed wavefront (poa_kernels_v4.cuh, default); 0: dp_rows_v3 (A/B switch)
 };
 
 // Static shared memory of the v3 kernel that is not part of the pool
@@ -1601,11 +1602,19 @@ __device__ void topsort_v3(const Win<SizeT>& g, const int32_t node_count, uint8_
 
 // needlemanWunschBanded (cudapoa_nw_banded.cuh:177-557) for one warp: band geometry as in nw_banded_v2, rows by dp_rows_v3,
 // end cell + traceback by traceback_tma (or traceback_plain when the pool is too small for the tile buffers).
+} // namespace poa
+} // namespace gwb200
+#include "poa_kernels_v4.cuh"
+namespace gwb200
+{
+namespace poa
+{
+
 template <typename ScoreT, typename SizeT, bool BULK>
 __device__ int32_t nw_banded_v3(const Win<SizeT>& g, int32_t graph_count, const uint8_t* read, int32_t read_length, ScoreT* scores,
                                 float max_buffer_size, SizeT* aln_graph, SizeT* aln_read, int32_t band_width, int32_t gap, int32_t mismatch,
                                 int32_t match, int32_t rerun, const bool Adaptive, unsigned long long& cells, int4* row_meta, uint8_t* pool,
-                                int32_t pool_bytes, unsigned long long* timers, V3Shared* sh, const int32_t tb_mode)
+                                int32_t pool_bytes, unsigned long long* timers, V3Shared* sh, const int32_t tb_mode, const int32_t wavefront)
 {
     GWB200_TIMER_START();
     const float gradient     = __fdividef(static_cast<float>(read_length + 1), static_cast<float>(graph_count + 1));
@@ -1647,7 +1656,15 @@ __device__ int32_t nw_banded_v3(const Win<SizeT>& g, int32_t graph_count, const 
         cells += static_cast<unsigned long long>(graph_count) * static_cast<unsigned long long>(band_width);
 
     Band<ScoreT> B{scores, band_width, band_shift, max_column, band_width + kRightPad, gradient};
-    dp_rows_v3<ScoreT, SizeT, BULK>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes, sh->rec[0]);
+    bool done = false;
+    if constexpr (sizeof(ScoreT) == 4)
+    {
+        if (wavefront != 0 && B.start(graph_count) < 65536)
+            done = dp_rows_v4<ScoreT, SizeT>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes,
+                                             sh->rec[0]);
+    }
+    if (!done)
+        dp_rows_v3<ScoreT, SizeT, BULK>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes, sh->rec[0]);
     GWB200_TIMER_LAP(0);
     int32_t result;
     if (tb_mode != 0 && pool_bytes >= TileBuf<ScoreT>::kBytes * 2)
@@ -1769,7 +1786,7 @@ __device__ void process_window_v3(const DeviceParams& P, const V2Extra& X, const
                 {
                     alen = nw_banded_v3<ScoreT, SizeT, BULK>(g, node_count, sequence, seq_len, scores, banded_buffer_size, aln_graph, aln_read,
                                                              P.band_width, P.gap, P.mismatch, P.match, rerun, adaptive, cells, row_meta, pool,
-                                                             X.pool_bytes, timers, sh, Y.tb_tma);
+                                                             X.pool_bytes, timers, sh, Y.tb_tma, Y.wavefront);
                     if (!adaptive || attempt == 1 || !(alen == kShiftLeft || alen == kShiftRight))
                         break;
                     rerun = alen; // rerun with extended and shifted band (cudapoa_kernels.cuh:374-396)
