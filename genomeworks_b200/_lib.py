@@ -76,6 +76,20 @@ def lib():
         L.gwb200_aligner_last_cells.restype = C.c_int64
         L.gwb200_aligner_last_kernel_ms.argtypes = [C.c_void_p]
         L.gwb200_aligner_last_kernel_ms.restype = C.c_float
+    if hasattr(L, "gwb200_global_aligner_create"):
+        L.gwb200_global_aligner_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gwb200_global_aligner_destroy.argtypes = [C.c_void_p]
+        L.gwb200_global_aligner_destroy.restype = None
+        L.gwb200_global_aligner_add_alignment.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
+        for name in ("align_all", "sync_alignments", "num_alignments", "reset"):
+            getattr(L, "gwb200_global_aligner_" + name).argtypes = [C.c_void_p]
+        L.gwb200_global_aligner_result_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.gwb200_global_aligner_result_states.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.gwb200_global_aligner_last_cells.argtypes = [C.c_void_p]
+        L.gwb200_global_aligner_last_cells.restype = C.c_int64
+        L.gwb200_global_aligner_last_kernel_ms.argtypes = [C.c_void_p]
+        L.gwb200_global_aligner_last_kernel_ms.restype = C.c_float
     _lib = L
     return L
 

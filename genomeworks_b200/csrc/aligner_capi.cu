@@ -567,3 +567,263 @@ float gwb200_aligner_last_kernel_ms(gwb200_aligner* a)
 }
 
 } // extern "C"
+
+// ================================================================================================================================
+// Fixed-size global aligners (AlignerGlobal family): Hirschberg-Myers and unbanded Myers. Host behaviour follows
+// cudaaligner/src/aligner_global.cpp:50-197 (fixed-stride staging, admission checks, result decoding); device code: global_kernels.cuh.
+// ================================================================================================================================
+#include "global_kernels.cuh"
+
+struct gwb200_global_aligner
+{
+    int32_t device_id   = 0;
+    cudaStream_t stream = nullptr;
+    int32_t algorithm   = 0;
+    int32_t max_query = 0, max_target = 0, max_alignments = 0;
+    int32_t max_len = 0, max_result_length = 0, pat_stride = 0;
+    int64_t leaf_elems    = 0;
+    int32_t col_smem_words = 0;
+    MemHooks hooks;
+    PinBuf<char> seq_h;
+    PinBuf<int32_t> len_h, res_len_h;
+    PinBuf<int8_t> res_h;
+    PinBuf<unsigned long long> cells_h;
+    DevBuf<char> seq_d;
+    DevBuf<int32_t> len_d, res_len_d, scores_d, leaf_sc_d;
+    DevBuf<int8_t> res_d;
+    DevBuf<galign::WordType> qpat_d, leaf_pv_d, leaf_mv_d, col_ws_d;
+    DevBuf<unsigned long long> cells_d;
+    int32_t n          = 0; // alignments added
+    int32_t n_launched = 0;
+    bool aligned = false, synced = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+extern "C" {
+
+int gwb200_global_aligner_create(gwb200_global_aligner** out, int32_t algorithm, int32_t max_query_length, int32_t max_target_length,
+                                 int32_t max_alignments, void* stream, int32_t device_id, gwb200_device_alloc_fn alloc,
+                                 gwb200_device_free_fn release, void* user)
+{
+    if (!out)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null output");
+    if (max_query_length < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_query_length must be non-negative.");
+    if (max_target_length < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_target_length must be non-negative.");
+    if (max_alignments < 0)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "max_alignments must be non-negative.");
+    if (max_alignments < 1)
+        return set_error(GWB200_E_RUNTIME, "Max alignments must be at least 1.");
+    if (algorithm != GWB200_GLOBAL_HIRSCHBERG_MYERS && algorithm != GWB200_GLOBAL_MYERS)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "unknown global alignment algorithm");
+    DeviceGuard guard(device_id);
+    auto* a            = new gwb200_global_aligner();
+    a->device_id       = device_id;
+    a->stream          = static_cast<cudaStream_t>(stream);
+    a->algorithm       = algorithm;
+    a->max_query       = max_query_length;
+    a->max_target      = max_target_length;
+    a->max_alignments  = max_alignments;
+    a->max_len         = std::max(max_query_length, max_target_length);
+    a->max_result_length = (max_query_length + max_target_length + 3) / 4 * 4; // calc_max_result_length, aligner_global.cpp:40-45
+    const int32_t max_nw = (max_query_length + 31) / 32;
+    a->pat_stride      = max_nw + 1;
+    // Hirschberg: leaf matrices of ceil(max_query / 32) * 64 words (aligner_global_hirschberg_myers.cpp:36-48);
+    // unbanded Myers: the whole matrix (aligner_global_myers.cpp:32-38)
+    a->leaf_elems = algorithm == GWB200_GLOBAL_MYERS ? static_cast<int64_t>(max_nw) * (max_target_length + 1) : static_cast<int64_t>(max_nw) * 64;
+    a->leaf_elems = std::max<int64_t>(a->leaf_elems, 1);
+    a->col_smem_words = std::min(max_nw + 1, 4096); // 2 x 16 KB of column state at most in shared memory
+    a->hooks.alloc   = alloc;
+    a->hooks.release = release;
+    a->hooks.user    = user;
+    a->seq_d.hooks = a->len_d.hooks = a->res_len_d.hooks = a->scores_d.hooks = a->leaf_sc_d.hooks = a->res_d.hooks = a->qpat_d.hooks =
+        a->leaf_pv_d.hooks = a->leaf_mv_d.hooks = a->col_ws_d.hooks = a->cells_d.hooks = &a->hooks;
+    const int64_t n = max_alignments;
+    bool ok = a->seq_h.ensure(2ll * a->max_len * n + 16, false) && a->len_h.ensure(2 * n, false) && a->res_len_h.ensure(n, false) &&
+              a->res_h.ensure(static_cast<int64_t>(a->max_result_length) * n + 16, false) && a->cells_h.ensure(1, false) &&
+              a->seq_d.ensure(2ll * a->max_len * n + 16) && a->len_d.ensure(2 * n) && a->res_len_d.ensure(n) &&
+              a->res_d.ensure(static_cast<int64_t>(a->max_result_length) * n + 16) && a->qpat_d.ensure(8ll * a->pat_stride * n) &&
+              a->scores_d.ensure(2ll * (max_target_length + 1) * n) && a->leaf_pv_d.ensure(a->leaf_elems * n) &&
+              a->leaf_mv_d.ensure(a->leaf_elems * n) && a->leaf_sc_d.ensure(a->leaf_elems * n) && a->col_ws_d.ensure(2ll * a->pat_stride * n) &&
+              a->cells_d.ensure(1);
+    if (!ok)
+    {
+        gwb200_global_aligner_destroy(a);
+        return set_error(GWB200_E_RUNTIME, "Out of memory.");
+    }
+    cudaEventCreate(&a->ev0);
+    cudaEventCreate(&a->ev1);
+    *out = a;
+    return 0;
+}
+
+void gwb200_global_aligner_destroy(gwb200_global_aligner* a)
+{
+    if (!a)
+        return;
+    DeviceGuard guard(a->device_id);
+    cudaStreamSynchronize(a->stream);
+    a->seq_d.release();
+    a->len_d.release();
+    a->res_len_d.release();
+    a->scores_d.release();
+    a->leaf_sc_d.release();
+    a->res_d.release();
+    a->qpat_d.release();
+    a->leaf_pv_d.release();
+    a->leaf_mv_d.release();
+    a->col_ws_d.release();
+    a->cells_d.release();
+    a->seq_h.release();
+    a->len_h.release();
+    a->res_len_h.release();
+    a->res_h.release();
+    a->cells_h.release();
+    if (a->ev0)
+        cudaEventDestroy(a->ev0);
+    if (a->ev1)
+        cudaEventDestroy(a->ev1);
+    delete a;
+}
+
+int gwb200_global_aligner_add_alignment(gwb200_global_aligner* a, const char* query, int32_t query_length, const char* target,
+                                        int32_t target_length, int32_t rc_q, int32_t rc_t)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    if (query_length < 0 || target_length < 0)
+        return GWB200_ALN_GENERIC_ERROR;
+    if (a->n >= a->max_alignments)
+        return GWB200_ALN_EXCEEDED_MAX_ALIGNMENTS;
+    if (query_length > a->max_query || target_length > a->max_target)
+        return GWB200_ALN_EXCEEDED_MAX_LENGTH;
+    static const char lookup[4] = {'T', 'G', 'A', 'C'}; // genomeutils::reverse_complement (utils/genomeutils.hpp:144-154)
+    auto stage = [&](char* dst, const char* src, int32_t len, int32_t rc) {
+        if (rc)
+            for (int32_t p = 0; p < len; ++p)
+                dst[p] = lookup[(static_cast<unsigned char>(src[len - 1 - p]) >> 1) & 0x3];
+        else
+            std::memcpy(dst, src, len);
+    };
+    stage(a->seq_h.p + static_cast<int64_t>(2 * a->n) * a->max_len, query, query_length, rc_q);
+    stage(a->seq_h.p + static_cast<int64_t>(2 * a->n + 1) * a->max_len, target, target_length, rc_t);
+    a->len_h.p[2 * a->n]     = query_length;
+    a->len_h.p[2 * a->n + 1] = target_length;
+    a->n++;
+    return GWB200_ALN_SUCCESS;
+}
+
+int gwb200_global_aligner_align_all(gwb200_global_aligner* a)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    if (a->n == 0)
+        return GWB200_ALN_SUCCESS;
+    DeviceGuard guard(a->device_id);
+    const int32_t n = a->n;
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->len_d.p, a->len_h.p, 8ll * n, cudaMemcpyHostToDevice, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->seq_d.p, a->seq_h.p, 2ll * a->max_len * n, cudaMemcpyHostToDevice, a->stream));
+    GWB200_CUDA_TRY(cudaMemsetAsync(a->cells_d.p, 0, 8, a->stream));
+    galign::GlobalParams P{};
+    P.seqs                 = a->seq_d.p;
+    P.seq_lengths          = a->len_d.p;
+    P.max_len              = a->max_len;
+    P.n_alignments         = n;
+    P.max_query_length     = a->max_query;
+    P.max_target_length    = a->max_target;
+    P.max_result_length    = a->max_result_length;
+    P.results              = a->res_d.p;
+    P.result_lengths       = a->res_len_d.p;
+    P.qpat                 = a->qpat_d.p;
+    P.pat_stride           = a->pat_stride;
+    P.scores               = a->scores_d.p;
+    P.leaf_pv              = a->leaf_pv_d.p;
+    P.leaf_mv              = a->leaf_mv_d.p;
+    P.leaf_sc              = a->leaf_sc_d.p;
+    P.leaf_elems           = a->leaf_elems;
+    P.col_ws               = a->col_ws_d.p;
+    P.col_smem_words       = a->col_smem_words;
+    P.full_myers_threshold = 63; // hirschberg_myers_switch_to_myers_size, aligner_global_hirschberg_myers.cpp:33
+    P.algorithm            = a->algorithm;
+    P.cells                = a->cells_d.p;
+    const int32_t smem     = 2 * a->col_smem_words * static_cast<int32_t>(sizeof(galign::WordType));
+    cudaEventRecord(a->ev0, a->stream);
+    galign::global_align_kernel<<<n, 32, smem, a->stream>>>(P);
+    count_launch();
+    cudaEventRecord(a->ev1, a->stream);
+    GWB200_CUDA_TRY(cudaGetLastError());
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->res_h.p, a->res_d.p, static_cast<int64_t>(a->max_result_length) * n, cudaMemcpyDeviceToHost, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->res_len_h.p, a->res_len_d.p, 4ll * n, cudaMemcpyDeviceToHost, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->cells_h.p, a->cells_d.p, 8, cudaMemcpyDeviceToHost, a->stream));
+    a->n_launched = n;
+    a->aligned    = true;
+    a->synced     = false;
+    return GWB200_ALN_SUCCESS;
+}
+
+int gwb200_global_aligner_sync_alignments(gwb200_global_aligner* a)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    DeviceGuard guard(a->device_id);
+    GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream));
+    a->synced = a->aligned;
+    return GWB200_ALN_SUCCESS;
+}
+
+int32_t gwb200_global_aligner_num_alignments(const gwb200_global_aligner* a) { return a ? a->n : 0; }
+
+int gwb200_global_aligner_result_info(const gwb200_global_aligner* a, int32_t i, int32_t* has_result, int32_t* is_optimal, int32_t* length)
+{
+    if (!a || i < 0 || i >= a->n)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "result index out of range");
+    int32_t len = 0;
+    bool have   = false;
+    if (a->synced && i < a->n_launched)
+    {
+        len  = a->res_len_h.p[i];
+        // aligner_global.cpp:180: an empty path counts only when both sequences are empty
+        have = len != 0 || (a->len_h.p[2 * i] == 0 && a->len_h.p[2 * i + 1] == 0);
+    }
+    if (has_result)
+        *has_result = have ? 1 : 0;
+    if (is_optimal)
+        *is_optimal = len >= 0 ? 1 : 0;
+    if (length)
+        *length = have ? std::abs(len) : 0;
+    return 0;
+}
+
+int gwb200_global_aligner_result_states(const gwb200_global_aligner* a, int32_t i, int8_t* states)
+{
+    if (!a || i < 0 || i >= a->n || !a->synced || i >= a->n_launched)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "no result");
+    const int32_t len    = std::abs(a->res_len_h.p[i]);
+    const int8_t* r      = a->res_h.p + static_cast<int64_t>(i) * a->max_result_length;
+    for (int32_t k = 0; k < len; ++k) // the device path runs end -> start (aligner_global.cpp:177)
+        states[k] = r[len - 1 - k];
+    return 0;
+}
+
+int gwb200_global_aligner_reset(gwb200_global_aligner* a)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    a->n          = 0;
+    a->n_launched = 0;
+    a->aligned    = false;
+    a->synced     = false;
+    return 0;
+}
+
+int64_t gwb200_global_aligner_last_cells(gwb200_global_aligner* a) { return a && a->synced ? static_cast<int64_t>(a->cells_h.p[0]) : 0; }
+float gwb200_global_aligner_last_kernel_ms(gwb200_global_aligner* a)
+{
+    float ms = 0.f;
+    if (a && a->synced)
+        cudaEventElapsedTime(&ms, a->ev0, a->ev1);
+    return ms;
+}
+
+} // extern "C"

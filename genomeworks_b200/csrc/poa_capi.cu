@@ -251,8 +251,14 @@ int32_t v3_pool_bytes(gwb200_poa_batch* b)
 template <typename ScoreT, typename SizeT>
 int32_t v3_action(gwb200_poa_batch* b, int action)
 {
-    const bool bulk    = b->Y.use_bulk != 0;
-    auto kfn           = bulk ? poa_window_kernel_v3<ScoreT, SizeT, true> : poa_window_kernel_v3<ScoreT, SizeT, false>;
+    // the wavefront rows (poa_kernels_v4.cuh, 32-bit scores) live in their own instantiation: its code and register budget
+    // do not weigh on the default kernel
+    auto kfn = poa_window_kernel_v3<ScoreT, SizeT, true, false>;
+    if constexpr (sizeof(ScoreT) == 4)
+    {
+        if (b->Y.wavefront != 0)
+            kfn = poa_window_kernel_v3<ScoreT, SizeT, true, true>;
+    }
     const int32_t smem = b->X.pool_bytes;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -807,6 +813,8 @@ static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void
             b->Y.use_bulk   = (e && std::atoi(e) == 0) ? 0 : 1;
             e               = std::getenv("GWB200_POA_TB_TMA");
             b->Y.tb_tma     = (e && std::atoi(e) == 0) ? 0 : 1;
+            e               = std::getenv("GWB200_POA_GROUP"); // development switch: chunks per straight-line group (4, 2, 1)
+            b->Y.max_group  = e ? std::atoi(e) : 2;
             e               = std::getenv("GWB200_POA_WAVEFRONT");
             b->Y.wavefront  = (e && std::atoi(e) != 0) ? 1 : 0; // off by default until it beats dp_rows_v3 (development switch)
         }

@@ -84,7 +84,8 @@ struct V3Extra
     int32_t* work_counter; // next window index (persistent grid), reset by the host before every launch
     int32_t use_bulk;      // 1: rows leave the ring by cp.async.bulk (default); 0: per-lane vector stores (A/B switch)
     int32_t tb_tma;        // 1: traceback tiles by bulk asynchronous copies with prefetch (default); 0: lane loads (A/B switch)
-    int32_t wavefront;     // 1: 32-bit score rows as a skewed wavefront (poa_kernels_v4.cuh, default); 0: dp_rows_v3 (A/B switch)
+    int32_t wavefront;     // 1: 32-bit score rows as a skewed wavefront (poa_kernels_v4.cuh); 0: dp_rows_v3 (default)
+    int32_t max_group;     // chunks per straight-line group of the row loop: 4, 2 or 1 (see dp_rows_v3)
 };
 
 // Static shared memory of the v3 kernel that is not part of the pool
@@ -183,6 +184,28 @@ __device__ __forceinline__ void closure_seq(int32_t (&s)[CPL], int32_t cin, int3
     left = L;
 }
 
+// The max-plus prefix scan of one chunk (the grouped row code below needs it for a minority of its chunks)
+template <int32_t CPL>
+__device__ __forceinline__ int32_t chunk_scan(int32_t (&a)[CPL], const int32_t cin, const int32_t gap, const int32_t lane)
+{
+    const int32_t gl = CPL * gap;
+    int32_t v        = a[CPL - 1] - gl * (lane + 1);
+#pragma unroll
+    for (int32_t d = 1; d < 32; d <<= 1)
+    {
+        const int32_t o = __shfl_up_sync(kFull, v, d);
+        if (lane >= d)
+            v = max(v, o);
+    }
+    int32_t excl    = __shfl_up_sync(kFull, v, 1);
+    excl            = (lane == 0) ? cin : max(cin, excl);
+    const int32_t L = excl + gl * lane;
+#pragma unroll
+    for (int32_t i = 0; i < CPL; i++)
+        a[i] = max(a[i], L + (i + 1) * gap);
+    return L;
+}
+
 // What a group of chunks needs to know about its row (fast rows: at most two predecessors, both in the ring)
 template <typename ScoreT>
 struct RowCtx
@@ -199,8 +222,8 @@ struct RowCtx
 // NJ consecutive chunks of one row, starting at chunk c0 (all of them exist: c0 + NJ <= number of chunks). Straight-line code:
 // every load of the group is issued before the first dependent instruction needs it. cin: carry into the first chunk (closed
 // value of the cell left of it), cleft: what is stored in that cell's place; both are updated for the next group.
-template <typename ScoreT, int32_t NJ, bool TWO>
-__device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int32_t c0, const int32_t lane, int32_t& cin, int32_t& cleft)
+template <typename ScoreT, int32_t NJ>
+__device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int32_t c0, const int32_t lane, int32_t& cin, int32_t& cleft, const bool TWO)
 {
     constexpr int32_t kMin = min_score_of<ScoreT>();
     constexpr int32_t CPL  = V3Cells<ScoreT>::kCPL;
@@ -213,8 +236,8 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
     {
         // ---- loads: read characters and the predecessors' units of every chunk
         uint32_t w[NJ][CPL / 4];
-        int32_t b0[NJ][CPL + 1], b1[TWO ? NJ : 1][CPL + 1];
-        bool in0[NJ], in1[TWO ? NJ : 1];
+        int32_t b0[NJ][CPL + 1], b1[NJ][CPL + 1];
+        bool in0[NJ], in1[NJ];
 #pragma unroll
         for (int32_t j = 0; j < NJ; j++)
         {
@@ -308,21 +331,7 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
         if (need[j] != 0u || cin + gap > s0l0[j])
         {
             // a horizontal run crosses a lane boundary (or enters from the chunk to the left): max-plus prefix scan over the lanes
-            const int32_t gl = CPL * gap;
-            int32_t v        = a[j][CPL - 1] - gl * (lane + 1);
-#pragma unroll
-            for (int32_t d = 1; d < 32; d <<= 1)
-            {
-                const int32_t o = __shfl_up_sync(kFull, v, d);
-                if (lane >= d)
-                    v = max(v, o);
-            }
-            int32_t excl    = __shfl_up_sync(kFull, v, 1);
-            excl            = (lane == 0) ? cin : max(cin, excl);
-            const int32_t L = excl + gl * lane;
-#pragma unroll
-            for (int32_t i = 0; i < CPL; i++)
-                a[j][i] = max(a[j][i], L + (i + 1) * gap);
+            const int32_t L = chunk_scan<CPL>(a[j], cin, gap, lane);
             if (lane != 0)
                 leftv[j] = L;
             const int32_t last_lane = min(31, (cx.bw - (c0 + j) * CH) / CPL - 1);
@@ -353,7 +362,7 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
 template <typename ScoreT, typename SizeT, bool BULK>
 __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const uint8_t* __restrict__ read, const Band<ScoreT>& B,
                            const int32_t band_width, const int32_t max_column, const int32_t gap, const int32_t mismatch, const int32_t match,
-                           int4* row_meta, uint8_t* pool, const int32_t pool_bytes, int4* srec)
+                           int4* row_meta, uint8_t* pool, const int32_t pool_bytes, int4* srec, const int32_t max_group)
 {
     constexpr int32_t kMin   = min_score_of<ScoreT>();
     constexpr int32_t CPL    = V3Cells<ScoreT>::kCPL;
@@ -523,32 +532,18 @@ __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const
                 cx.gap   = gap;
                 cx.match = match;
                 cx.mismatch = mismatch;
-                for (int32_t c0 = 0; c0 < nchunks; c0 += GC)
-                {
-                    const int32_t nj = min(GC, nchunks - c0);
-                    if (pc == 2)
-                    {
-                        if (nj >= 4)
-                            row_group_v3<ScoreT, (GC >= 4 ? 4 : GC), true>(cx, c0, lane, cin, cleft);
-                        else if (nj == 3)
-                            row_group_v3<ScoreT, (GC >= 3 ? 3 : GC), true>(cx, c0, lane, cin, cleft);
-                        else if (nj == 2)
-                            row_group_v3<ScoreT, 2, true>(cx, c0, lane, cin, cleft);
-                        else
-                            row_group_v3<ScoreT, 1, true>(cx, c0, lane, cin, cleft);
-                    }
-                    else
-                    {
-                        if (nj >= 4)
-                            row_group_v3<ScoreT, (GC >= 4 ? 4 : GC), false>(cx, c0, lane, cin, cleft);
-                        else if (nj == 3)
-                            row_group_v3<ScoreT, (GC >= 3 ? 3 : GC), false>(cx, c0, lane, cin, cleft);
-                        else if (nj == 2)
-                            row_group_v3<ScoreT, 2, false>(cx, c0, lane, cin, cleft);
-                        else
-                            row_group_v3<ScoreT, 1, false>(cx, c0, lane, cin, cleft);
-                    }
-                }
+                // group sizes 4, 2, 1 only (one instantiation each, the second predecessor is a run-time flag): what the row loop
+                // executes has to stay resident in the instruction cache with 10+ windows per SM at different places
+                const bool two = pc == 2;
+                int32_t c0     = 0;
+                if (GC >= 4 && max_group >= 4)
+                    for (; c0 + 4 <= nchunks; c0 += 4)
+                        row_group_v3<ScoreT, (GC >= 4 ? 4 : 1)>(cx, c0, lane, cin, cleft, two);
+                if (max_group >= 2)
+                    for (; c0 + 2 <= nchunks; c0 += 2)
+                        row_group_v3<ScoreT, 2>(cx, c0, lane, cin, cleft, two);
+                for (; c0 < nchunks; c0++)
+                    row_group_v3<ScoreT, 1>(cx, c0, lane, cin, cleft, two);
             }
             else
             {
@@ -1610,11 +1605,11 @@ namespace gwb200
 namespace poa
 {
 
-template <typename ScoreT, typename SizeT, bool BULK>
+template <typename ScoreT, typename SizeT, bool BULK, bool WAVE>
 __device__ int32_t nw_banded_v3(const Win<SizeT>& g, int32_t graph_count, const uint8_t* read, int32_t read_length, ScoreT* scores,
                                 float max_buffer_size, SizeT* aln_graph, SizeT* aln_read, int32_t band_width, int32_t gap, int32_t mismatch,
                                 int32_t match, int32_t rerun, const bool Adaptive, unsigned long long& cells, int4* row_meta, uint8_t* pool,
-                                int32_t pool_bytes, unsigned long long* timers, V3Shared* sh, const int32_t tb_mode, const int32_t wavefront)
+                                int32_t pool_bytes, unsigned long long* timers, V3Shared* sh, const int32_t tb_mode, const int32_t wavefront, const int32_t max_group)
 {
     GWB200_TIMER_START();
     const float gradient     = __fdividef(static_cast<float>(read_length + 1), static_cast<float>(graph_count + 1));
@@ -1657,14 +1652,14 @@ __device__ int32_t nw_banded_v3(const Win<SizeT>& g, int32_t graph_count, const 
 
     Band<ScoreT> B{scores, band_width, band_shift, max_column, band_width + kRightPad, gradient};
     bool done = false;
-    if constexpr (sizeof(ScoreT) == 4)
+    if constexpr (WAVE && sizeof(ScoreT) == 4)
     {
         if (wavefront != 0 && B.start(graph_count) < 65536)
             done = dp_rows_v4<ScoreT, SizeT>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes,
                                              sh->rec[0]);
     }
     if (!done)
-        dp_rows_v3<ScoreT, SizeT, BULK>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes, sh->rec[0]);
+        dp_rows_v3<ScoreT, SizeT, BULK>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes, sh->rec[0], max_group);
     GWB200_TIMER_LAP(0);
     int32_t result;
     if (tb_mode != 0 && pool_bytes >= TileBuf<ScoreT>::kBytes * 2)
@@ -1678,7 +1673,7 @@ __device__ int32_t nw_banded_v3(const Win<SizeT>& g, int32_t graph_count, const 
 }
 
 // One window from the backbone to the consensus / MSA (cudapoa_kernels.cuh:200-541) on one warp.
-template <typename ScoreT, typename SizeT, bool BULK>
+template <typename ScoreT, typename SizeT, bool BULK, bool WAVE>
 __device__ void process_window_v3(const DeviceParams& P, const V2Extra& X, const V3Extra& Y, const int32_t w, uint8_t* pool, V3Shared* sh)
 {
     const bool MSA      = P.msa != 0;
@@ -1784,9 +1779,9 @@ __device__ void process_window_v3(const DeviceParams& P, const V2Extra& X, const
                 int32_t rerun       = 0;
                 for (int32_t attempt = 0; attempt < 2; attempt++)
                 {
-                    alen = nw_banded_v3<ScoreT, SizeT, BULK>(g, node_count, sequence, seq_len, scores, banded_buffer_size, aln_graph, aln_read,
+                    alen = nw_banded_v3<ScoreT, SizeT, BULK, WAVE>(g, node_count, sequence, seq_len, scores, banded_buffer_size, aln_graph, aln_read,
                                                              P.band_width, P.gap, P.mismatch, P.match, rerun, adaptive, cells, row_meta, pool,
-                                                             X.pool_bytes, timers, sh, Y.tb_tma, Y.wavefront);
+                                                             X.pool_bytes, timers, sh, Y.tb_tma, Y.wavefront, Y.max_group);
                     if (!adaptive || attempt == 1 || !(alen == kShiftLeft || alen == kShiftRight))
                         break;
                     rerun = alen; // rerun with extended and shifted band (cudapoa_kernels.cuh:374-396)
@@ -1858,8 +1853,8 @@ __device__ void process_window_v3(const DeviceParams& P, const V2Extra& X, const
 }
 
 // Persistent grid: one warp per CTA, every CTA pulls window indices from the batch's work counter until none is left.
-template <typename ScoreT, typename SizeT, bool BULK>
-__global__ void __launch_bounds__(32, (sizeof(ScoreT) == 4 ? 12 : 16)) poa_window_kernel_v3(const DeviceParams P, const V2Extra X, const V3Extra Y)
+template <typename ScoreT, typename SizeT, bool BULK, bool WAVE>
+__global__ void __launch_bounds__(32, (WAVE ? 8 : (sizeof(ScoreT) == 4 ? 12 : 16))) poa_window_kernel_v3(const DeviceParams P, const V2Extra X, const V3Extra Y)
 {
     extern __shared__ __align__(16) uint8_t pool[];
     __shared__ __align__(16) V3Shared sh;
@@ -1881,7 +1876,7 @@ __global__ void __launch_bounds__(32, (sizeof(ScoreT) == 4 ? 12 : 16)) poa_windo
         w = __shfl_sync(kFull, w, 0);
         if (w >= P.n_windows)
             break;
-        process_window_v3<ScoreT, SizeT, BULK>(P, X, Y, w, pool, &sh);
+        process_window_v3<ScoreT, SizeT, BULK, WAVE>(P, X, Y, w, pool, &sh);
     }
 }
 

@@ -320,90 +320,153 @@ __device__ bool dp_rows_v4(const Win<SizeT>& g, const int32_t graph_count, const
         npend = 0;
     };
 
-    auto step = [&]() {
+    // U consecutive iterations of every lane as one straight-line piece: all loads of the U groups (read characters,
+    // predecessor groups) are issued before the first dependent instruction, only the horizontal carry runs serially
+    // through the 4 * U cells. Legal because what iteration it + k reads was written at iteration it + k - d * S4 <= it - 1
+    // for U <= S4; the caller also keeps a chunk inside one block of 8 slots (write-back granularity).
+    auto chunk = [&](auto UC) {
+        constexpr int32_t U = decltype(UC)::value;
         __syncwarp();
         if (cnt > 0)
         {
-            const uint32_t w = __ldg(read32 + (it + rdoff));
-            const int32_t q0 = (static_cast<int32_t>(w & 0xffu) == base) ? match : mismatch;
-            const int32_t q1 = (static_cast<int32_t>((w >> 8) & 0xffu) == base) ? match : mismatch;
-            const int32_t q2 = (static_cast<int32_t>((w >> 16) & 0xffu) == base) ? match : mismatch;
-            const int32_t q3 = (static_cast<int32_t>(w >> 24) == base) ? match : mismatch;
-            int32_t t0, t1, t2, t3;
-            if (it <= i_inv)
+            uint32_t w[U];
+            int4 v0[U], v1[U], v2[U];
+            int32_t m0[U], m1[U], m2[U];
+#pragma unroll
+            for (int32_t k = 0; k < U; k++)
             {
-                int32_t so = sl - ko0;
+                w[k]       = (k < cnt) ? __ldg(read32 + (it + k + rdoff)) : 0u;
+                int32_t so = sl + k - ko0;
                 so += (so >> 31) & Wg;
-                const int4 v = lds128(pw4_0 + (so << 4));
-                int32_t M0 = v.x, M1 = v.y, M2 = v.z, M3 = v.w;
-                int32_t M4 = lds32(ps3_0 + (so << 2));
-                if (npass >= 2)
+                v0[k] = lds128(pw4_0 + (so << 4));
+                m0[k] = lds32(ps3_0 + (so << 2));
+            }
+            if (npass >= 2)
+            {
+#pragma unroll
+                for (int32_t k = 0; k < U; k++)
                 {
-                    int32_t s1 = sl - ko1;
-                    s1 += (s1 >> 31) & Wg;
-                    const int4 u     = lds128(pw4_1 + (s1 << 4));
-                    const int32_t u4 = lds32(ps3_1 + (s1 << 2));
-                    if (npass >= 3)
+                    int32_t so = sl + k - ko1;
+                    so += (so >> 31) & Wg;
+                    v1[k] = lds128(pw4_1 + (so << 4));
+                    m1[k] = lds32(ps3_1 + (so << 2));
+                }
+                if (npass >= 3)
+                {
+#pragma unroll
+                    for (int32_t k = 0; k < U; k++)
                     {
-                        int32_t s2 = sl - ko2;
-                        s2 += (s2 >> 31) & Wg;
-                        const int4 x     = lds128(pw4_2 + (s2 << 4));
-                        const int32_t x4 = lds32(ps3_2 + (s2 << 2));
-                        M0               = __vimax3_s32(M0, u.x, x.x);
-                        M1               = __vimax3_s32(M1, u.y, x.y);
-                        M2               = __vimax3_s32(M2, u.z, x.z);
-                        M3               = __vimax3_s32(M3, u.w, x.w);
-                        M4               = __vimax3_s32(M4, u4, x4);
+                        int32_t so = sl + k - ko2;
+                        so += (so >> 31) & Wg;
+                        v2[k] = lds128(pw4_2 + (so << 4));
+                        m2[k] = lds32(ps3_2 + (so << 2));
+                    }
+#pragma unroll
+                    for (int32_t k = 0; k < U; k++)
+                    {
+                        v0[k].x = __vimax3_s32(v0[k].x, v1[k].x, v2[k].x);
+                        v0[k].y = __vimax3_s32(v0[k].y, v1[k].y, v2[k].y);
+                        v0[k].z = __vimax3_s32(v0[k].z, v1[k].z, v2[k].z);
+                        v0[k].w = __vimax3_s32(v0[k].w, v1[k].w, v2[k].w);
+                        m0[k]   = __vimax3_s32(m0[k], m1[k], m2[k]);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int32_t k = 0; k < U; k++)
+                    {
+                        v0[k].x = max(v0[k].x, v1[k].x);
+                        v0[k].y = max(v0[k].y, v1[k].y);
+                        v0[k].z = max(v0[k].z, v1[k].z);
+                        v0[k].w = max(v0[k].w, v1[k].w);
+                        m0[k]   = max(m0[k], m1[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int32_t k = 0; k < U; k++)
+            {
+                if (k < cnt)
+                {
+                    const int32_t q0 = (static_cast<int32_t>(w[k] & 0xffu) == base) ? match : mismatch;
+                    const int32_t q1 = (static_cast<int32_t>((w[k] >> 8) & 0xffu) == base) ? match : mismatch;
+                    const int32_t q2 = (static_cast<int32_t>((w[k] >> 16) & 0xffu) == base) ? match : mismatch;
+                    const int32_t q3 = (static_cast<int32_t>(w[k] >> 24) == base) ? match : mismatch;
+                    int32_t t0, t1, t2, t3;
+                    if (it + k <= i_inv)
+                    {
+                        t0 = __viaddmax_s32(v0[k].y, gap, v0[k].x + q0);
+                        t1 = __viaddmax_s32(v0[k].z, gap, v0[k].y + q1);
+                        t2 = __viaddmax_s32(v0[k].w, gap, v0[k].z + q2);
+                        t3 = __viaddmax_s32(m0[k], gap, v0[k].w + q3);
                     }
                     else
                     {
-                        M0 = max(M0, u.x);
-                        M1 = max(M1, u.y);
-                        M2 = max(M2, u.z);
-                        M3 = max(M3, u.w);
-                        M4 = max(M4, u4);
+                        const int4 t = wf_general<ScoreT, SizeT>(C, row, node, bs, it + k + rdoff - (bs >> 2), sl + k, q0, q1, q2, q3);
+                        t0           = t.x;
+                        t1           = t.y;
+                        t2           = t.z;
+                        t3           = t.w;
                     }
+                    const int32_t s0 = __viaddmax_s32(carry, gap, t0);
+                    const int32_t s1 = __viaddmax_s32(s0, gap, t1);
+                    const int32_t s2 = __viaddmax_s32(s1, gap, t2);
+                    const int32_t s3 = __viaddmax_s32(s2, gap, t3);
+                    sts128(own4 + ((sl + k) << 4), stl, s0, s1, s2);
+                    sts32(own1 + ((sl + k) << 2), s3);
+                    stl   = s3;
+                    carry = s3;
                 }
-                t0 = __viaddmax_s32(M1, gap, M0 + q0);
-                t1 = __viaddmax_s32(M2, gap, M1 + q1);
-                t2 = __viaddmax_s32(M3, gap, M2 + q2);
-                t3 = __viaddmax_s32(M4, gap, M3 + q3);
             }
-            else
-            {
-                const int4 t = wf_general<ScoreT, SizeT>(C, row, node, bs, it + rdoff - (bs >> 2), sl, q0, q1, q2, q3);
-                t0           = t.x;
-                t1           = t.y;
-                t2           = t.z;
-                t3           = t.w;
-            }
-            const int32_t s0 = __viaddmax_s32(carry, gap, t0);
-            const int32_t s1 = __viaddmax_s32(s0, gap, t1);
-            const int32_t s2 = __viaddmax_s32(s1, gap, t2);
-            const int32_t s3 = __viaddmax_s32(s2, gap, t3);
-            sts128(own4 + (sl << 4), stl, s0, s1, s2);
-            sts32(own1 + (sl << 2), s3);
-            stl   = s3;
-            carry = s3;
+            const int32_t done = min(cnt, U);
             if (npend == 0)
                 pend0 = sl;
-            npend++;
-            cnt--;
+            npend += done;
+            cnt -= done;
             if (cnt == 0)
             {
                 // last real cell (local band_width) + right padding, straight to HBM (:158-175)
                 ScoreT* const tail                 = scores + static_cast<int64_t>(row) * stride + band_width;
-                *reinterpret_cast<int4*>(tail)     = make_int4(s3, kMin, kMin, kMin);
+                *reinterpret_cast<int4*>(tail)     = make_int4(carry, kMin, kMin, kMin);
                 *reinterpret_cast<int4*>(tail + 4) = make_int4(kMin, kMin, kMin, kMin);
             }
         }
-        if ((sl & 7) == 7)
+        it += U;
+        sl += U;
+        if (sl == Wg)
+            sl = 0;
+        if ((sl & 7) == 0)
         {
             __syncwarp();
             flush();
         }
-        it++;
-        sl = (sl + 1 == Wg) ? 0 : sl + 1;
+    };
+    const int32_t umax = min(4, S4);
+    // advance to iteration `until` (or, with until < 0, until no lane has work left)
+    auto run_to = [&](int32_t until) {
+        for (;;)
+        {
+            int32_t n = min(umax, 8 - (sl & 7));
+            if (until >= 0)
+            {
+                if (it >= until)
+                    break;
+                n = min(n, until - it);
+            }
+            else if (!__any_sync(kFull, cnt > 0))
+            {
+                break;
+            }
+            if (n >= 4)
+                chunk(std::integral_constant<int32_t, 4>{});
+            else if (n == 3)
+                chunk(std::integral_constant<int32_t, 3>{});
+            else if (n == 2)
+                chunk(std::integral_constant<int32_t, 2>{});
+            else
+                chunk(std::integral_constant<int32_t, 1>{});
+        }
     };
 
     // iteration at which row 1 starts
@@ -449,8 +512,7 @@ __device__ bool dp_rows_v4(const Win<SizeT>& g, const int32_t graph_count, const
         const int4 rc     = srec[(r - 1) & 63];
         const int32_t rbs = rc.x & 0xffff;
         const int32_t I_r = r * S4 + (rbs >> 2);
-        while (it < I_r)
-            step();
+        run_to(I_r);
         __syncwarp();
         if (lane == (r & 31))
         {
@@ -498,8 +560,7 @@ __device__ bool dp_rows_v4(const Win<SizeT>& g, const int32_t graph_count, const
         __syncwarp();
         npass = __reduce_max_sync(kFull, cnt > 0 ? pc3 : 0);
     }
-    while (__any_sync(kFull, cnt > 0))
-        step();
+    run_to(-1);
     __syncwarp();
     // ---- everything that is still in the windows; the traceback reads HBM
     flush();

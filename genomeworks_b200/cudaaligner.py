@@ -208,6 +208,94 @@ class FixedBandAligner:
             pass
 
 
+def _rle(states):
+    """expanded AlignmentState bytes -> (actions, runlengths)"""
+    s = np.asarray(states, dtype=np.int8)
+    if s.size == 0:
+        return np.zeros(0, np.int8), np.zeros(0, np.int32)
+    cut = np.flatnonzero(np.diff(s)) + 1
+    starts = np.concatenate(([0], cut))
+    ends = np.concatenate((cut, [s.size]))
+    return s[starts].copy(), (ends - starts).astype(np.int32)
+
+
+class GlobalAligner:
+    """The fixed-size global aligners behind the deprecated factory create_aligner(max_query_length, max_target_length,
+    max_alignments, ...) (aligner.hpp:183,196 -> AlignerGlobalHirschbergMyers, cudaaligner/src/aligner.cpp:31-74) and the in-library
+    unbanded AlignerGlobalMyers. Host semantics = AlignerGlobal (cudaaligner/src/aligner_global.cpp:50-197)."""
+
+    ALGORITHMS = {"hirschberg_myers": 0, "myers": 1}
+
+    def __init__(self, max_query_length, max_target_length, max_alignments, algorithm="hirschberg_myers", stream=None, device_id=0):
+        self._h = C.c_void_p()
+        st = None
+        if stream is not None:
+            st = stream.stream if hasattr(stream, "stream") else stream.cuda_stream
+        self.stream = stream
+        self._alignments = []
+        self._first_unsynced = 0
+        check(lib().gwb200_global_aligner_create(C.byref(self._h), C.c_int32(self.ALGORITHMS[algorithm]), C.c_int32(max_query_length),
+                                                 C.c_int32(max_target_length), C.c_int32(max_alignments), C.c_void_p(st), C.c_int32(device_id),
+                                                 None, None, None))
+
+    def add_alignment(self, query, target, reverse_complement_query=False, reverse_complement_target=False):
+        q = query.encode("utf-8") if isinstance(query, str) else bytes(query)
+        t = target.encode("utf-8") if isinstance(target, str) else bytes(target)
+        rc = check(lib().gwb200_global_aligner_add_alignment(self._h, q, C.c_int32(len(q)), t, C.c_int32(len(t)),
+                                                             C.c_int32(1 if reverse_complement_query else 0),
+                                                             C.c_int32(1 if reverse_complement_target else 0)))
+        if rc == success:
+            # the Alignment exists from here on, status uninitialized until sync_alignments (aligner_global.cpp:131-138)
+            qa = _revcomp(q) if reverse_complement_query else q
+            ta = _revcomp(t) if reverse_complement_target else t
+            self._alignments.append(Alignment(qa.decode(), ta.decode(), uninitialized, False, np.zeros(0, np.int8), np.zeros(0, np.int32)))
+        return rc
+
+    def align_all(self):
+        return check(lib().gwb200_global_aligner_align_all(self._h))
+
+    def sync_alignments(self):
+        rc = check(lib().gwb200_global_aligner_sync_alignments(self._h))
+        have, opt, n = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        for i, al in enumerate(self._alignments):
+            check(lib().gwb200_global_aligner_result_info(self._h, C.c_int32(i), C.byref(have), C.byref(opt), C.byref(n)))
+            if not have.value:
+                continue
+            st = np.zeros(max(n.value, 1), dtype=np.int8)
+            check(lib().gwb200_global_aligner_result_states(self._h, C.c_int32(i), st.ctypes.data))
+            al.actions, al.runlengths = _rle(st[:n.value])
+            al.is_optimal = bool(opt.value)
+            al.status = success
+        return rc
+
+    def get_alignments(self):
+        return list(self._alignments)
+
+    def num_alignments(self):
+        return len(self._alignments)
+
+    def reset(self):
+        self._alignments = []
+        check(lib().gwb200_global_aligner_reset(self._h))
+
+    def last_cells(self):
+        return int(lib().gwb200_global_aligner_last_cells(self._h))
+
+    def last_kernel_ms(self):
+        return float(lib().gwb200_global_aligner_last_kernel_ms(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().gwb200_global_aligner_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class CudaAlignerBatch:
     """pygenomeworks.CudaAlignerBatch (cudaaligner.pyx:129-260): deprecated-factory signature."""
 
@@ -220,18 +308,13 @@ class CudaAlignerBatch:
         self.max_query_length = max_query_length
         self.max_target_length = max_target_length
         self.max_alignments = max_alignments
-        bw = max(max_query_length, max_target_length, 2)
-        if bw % 32 == 1:
-            bw += 1
-        self._aligner = FixedBandAligner(bw, stream=stream, device_id=device_id, max_device_memory=max_device_memory_allocator_caching_size)
+        # the deprecated factory builds AlignerGlobalHirschbergMyers (cudaaligner/src/aligner.cpp:31-74)
+        if max_device_memory_allocator_caching_size < -1:
+            raise ValueError("max_device_memory_allocator_caching_size has to be either -1 (=all available GPU memory) or greater or equal than 0.")
+        self._aligner = GlobalAligner(max_query_length, max_target_length, max_alignments, "hirschberg_myers", stream=stream, device_id=device_id)
         self.stream = stream
 
     def add_alignment(self, query, target):
-        # AlignerGlobal::add_alignment admission (cudaaligner/src/aligner_global.cpp:50-86)
-        if len(query) > self.max_query_length or len(target) > self.max_target_length:
-            return exceeded_max_length
-        if self._aligner.num_alignments() >= self.max_alignments:
-            return exceeded_max_alignments
         return self._aligner.add_alignment(query, target)
 
     def align_all(self):

@@ -246,6 +246,113 @@ private:
     std::vector<std::shared_ptr<Alignment>> alignments_;
 };
 
+/// AlignerGlobal (cudaaligner/src/aligner_global.hpp:40-127) on this engine: fixed maximum lengths / count, Hirschberg-Myers
+/// (what the reference's deprecated factory builds, cudaaligner/src/aligner.cpp:31-74) or the unbanded Myers aligner.
+class AlignerGlobalB200 : public Aligner
+{
+public:
+    AlignerGlobalB200(int32_t algorithm, int32_t max_query_length, int32_t max_target_length, int32_t max_alignments, cudaStream_t stream,
+                      int32_t device_id)
+        : stream_(stream)
+        , device_(device_id)
+    {
+        check(gwb200_global_aligner_create(&h_, algorithm, max_query_length, max_target_length, max_alignments, stream, device_id, nullptr,
+                                           nullptr, nullptr));
+    }
+    AlignerGlobalB200(int32_t algorithm, int32_t max_query_length, int32_t max_target_length, int32_t max_alignments,
+                      DefaultDeviceAllocator allocator, cudaStream_t stream, int32_t device_id)
+        : stream_(stream)
+        , device_(device_id)
+        , allocator_(allocator)
+    {
+        check(gwb200_global_aligner_create(&h_, algorithm, max_query_length, max_target_length, max_alignments, stream, device_id,
+                                           &AlignerGlobalB200::pool_alloc, &AlignerGlobalB200::pool_free, this));
+    }
+    ~AlignerGlobalB200() override { gwb200_global_aligner_destroy(h_); }
+    AlignerGlobalB200(const AlignerGlobalB200&) = delete;
+    AlignerGlobalB200& operator=(const AlignerGlobalB200&) = delete;
+
+    StatusType add_alignment(const char* query, int32_t query_length, const char* target, int32_t target_length, bool rc_q = false,
+                             bool rc_t = false) override
+    {
+        const int rc = check(gwb200_global_aligner_add_alignment(h_, query, query_length, target, target_length, rc_q ? 1 : 0, rc_t ? 1 : 0));
+        if (rc == success)
+        {
+            // the Alignment exists from here on (aligner_global.cpp:131-138) and carries the sequences as they are aligned
+            auto al = std::make_shared<AlignmentB200>(AlignerB200::staged(query, query_length, rc_q), AlignerB200::staged(target, target_length, rc_t));
+            al->set_type(AlignmentType::global_alignment);
+            alignments_.push_back(std::move(al));
+        }
+        return static_cast<StatusType>(rc);
+    }
+    StatusType align_all() override { return static_cast<StatusType>(check(gwb200_global_aligner_align_all(h_))); }
+    StatusType sync_alignments() override
+    {
+        const int rc = check(gwb200_global_aligner_sync_alignments(h_));
+        for (int32_t i = 0; i < static_cast<int32_t>(alignments_.size()); ++i)
+        {
+            int32_t have = 0, opt = 0, n = 0;
+            check(gwb200_global_aligner_result_info(h_, i, &have, &opt, &n));
+            if (!have)
+                continue; // failed alignment: the object stays as add_alignment made it (aligner_global.cpp:180)
+            std::vector<int8_t> st(std::max(n, 1));
+            check(gwb200_global_aligner_result_states(h_, i, st.data()));
+            st.resize(n);
+            std::vector<int8_t> actions;
+            std::vector<int32_t> runs;
+            for (int32_t k = 0; k < n; ++k)
+            {
+                if (actions.empty() || actions.back() != st[k])
+                {
+                    actions.push_back(st[k]);
+                    runs.push_back(0);
+                }
+                ++runs.back();
+            }
+            AlignmentB200* al = static_cast<AlignmentB200*>(alignments_[i].get());
+            al->set(StatusType::success, opt != 0, std::move(actions), std::move(runs));
+            al->expand();
+        }
+        return static_cast<StatusType>(rc);
+    }
+    const std::vector<std::shared_ptr<Alignment>>& get_alignments() const override { return alignments_; }
+    /// AlignerGlobal::get_alignments_device (aligner_global.hpp:78-83): not available for this aligner family
+    DeviceAlignmentsPtrs get_alignments_device() const override { throw std::runtime_error("get_alignments_device() not implemented for this aligner"); }
+    void reset() override
+    {
+        check(gwb200_global_aligner_reset(h_));
+        alignments_.clear();
+    }
+    void free_temporary_device_buffers() override {}
+    int32_t num_alignments() const override { return static_cast<int32_t>(alignments_.size()); }
+    cudaStream_t get_stream() const override { return stream_; }
+    int32_t get_device() const override { return device_; }
+    DefaultDeviceAllocator get_device_allocator() const override { return allocator_; }
+
+private:
+    static void* pool_alloc(void* user, int64_t bytes)
+    {
+        AlignerGlobalB200* self = static_cast<AlignerGlobalB200*>(user);
+        try
+        {
+            return self->allocator_.allocate(static_cast<std::size_t>(bytes), {self->stream_});
+        }
+        catch (const device_memory_allocation_exception&)
+        {
+            return nullptr;
+        }
+    }
+    static void pool_free(void* user, void* ptr, int64_t bytes)
+    {
+        static_cast<AlignerGlobalB200*>(user)->allocator_.deallocate(static_cast<char*>(ptr), static_cast<std::size_t>(bytes));
+    }
+    gwb200_global_aligner* h_ = nullptr;
+    cudaStream_t stream_;
+    int32_t device_;
+    DefaultDeviceAllocator allocator_;
+    std::vector<std::shared_ptr<Alignment>> alignments_;
+};
+
 inline int32_t covering_bandwidth(int32_t max_query_length, int32_t max_target_length)
 {
     int32_t bw = std::max(std::max(max_query_length, max_target_length), 2);
@@ -255,15 +362,14 @@ inline int32_t covering_bandwidth(int32_t max_query_length, int32_t max_target_l
 }
 } // namespace detail
 
-/// Deprecated factory (aligner.hpp:183): fixed maximum lengths / count.
+/// Deprecated factory (aligner.hpp:183): fixed maximum lengths / count -> AlignerGlobalHirschbergMyers (cudaaligner/src/aligner.cpp:31-74).
 inline std::unique_ptr<Aligner> create_aligner(int32_t max_query_length, int32_t max_target_length, int32_t max_alignments, AlignmentType type,
                                                DefaultDeviceAllocator allocator, cudaStream_t stream, int32_t device_id)
 {
     if (type != AlignmentType::global_alignment)
         throw std::runtime_error("Aligner for specified type not implemented yet.");
-    return std::unique_ptr<Aligner>(new detail::AlignerB200(detail::covering_bandwidth(max_query_length, max_target_length), stream, device_id,
-                                                            allocator, allocator.get_size_of_largest_free_memory_block(), max_query_length,
-                                                            max_target_length, max_alignments));
+    return std::unique_ptr<Aligner>(new detail::AlignerGlobalB200(GWB200_GLOBAL_HIRSCHBERG_MYERS, max_query_length, max_target_length, max_alignments,
+                                                                  allocator, stream, device_id));
 }
 /// Deprecated factory (aligner.hpp:196).
 inline std::unique_ptr<Aligner> create_aligner(int32_t max_query_length, int32_t max_target_length, int32_t max_alignments, AlignmentType type,
@@ -273,9 +379,8 @@ inline std::unique_ptr<Aligner> create_aligner(int32_t max_query_length, int32_t
         throw std::runtime_error("Aligner for specified type not implemented yet.");
     if (max_device_memory_allocator_caching_size < -1)
         throw std::invalid_argument("max_device_memory_allocator_caching_size has to be either -1 (=all available GPU memory) or greater or equal than 0.");
-    return std::unique_ptr<Aligner>(new detail::AlignerB200(detail::covering_bandwidth(max_query_length, max_target_length), stream, device_id,
-                                                            max_device_memory_allocator_caching_size, max_query_length, max_target_length,
-                                                            max_alignments));
+    return std::unique_ptr<Aligner>(new detail::AlignerGlobalB200(GWB200_GLOBAL_HIRSCHBERG_MYERS, max_query_length, max_target_length, max_alignments,
+                                                                  stream, device_id));
 }
 /// FixedBand factory with allocator (aligner.hpp:208): max_device_memory == -1 => the allocator's largest free block.
 inline std::unique_ptr<FixedBandAligner> create_aligner(AlignmentType type, int32_t max_bandwidth, cudaStream_t stream, int32_t device_id,

@@ -261,6 +261,41 @@ int64_t gwb200_aligner_last_cells(gwb200_aligner* aligner);
 float gwb200_aligner_last_kernel_ms(gwb200_aligner* aligner);
 
 /* ------------------------------------------------------------------------------------------------
+ * cudaaligner, fixed-size global aligners: what the deprecated factory create_aligner(max_query_length, max_target_length,
+ * max_alignments, type, [allocator,] stream, device) builds (cudaaligner/include/.../aligner.hpp:183,196; src/aligner.cpp:31-74
+ * -> AlignerGlobalHirschbergMyers) and the in-library AlignerGlobalMyers (cudaaligner/src/aligner_global_myers.cpp).
+ * Host behaviour = AlignerGlobal (cudaaligner/src/aligner_global.cpp:50-197): fixed-stride sequence and result slots,
+ * results as one AlignmentState byte per alignment column in forward order.
+ * ---------------------------------------------------------------------------------------------- */
+enum gwb200_global_algorithm
+{
+    GWB200_GLOBAL_HIRSCHBERG_MYERS = 0, /* aligner_global_hirschberg_myers.cpp:32-75, hirschberg_myers_gpu.cu:575-699 */
+    GWB200_GLOBAL_MYERS            = 1  /* aligner_global_myers.cpp:40-70, myers_gpu.cu:256-442,1117-1139 */
+};
+typedef struct gwb200_global_aligner gwb200_global_aligner; /* opaque: one cudaaligner::AlignerGlobal */
+
+/* AlignerGlobal::AlignerGlobal (aligner_global.cpp:50-76): negative sizes -> GWB200_E_INVALID_ARGUMENT, max_alignments < 1 ->
+ * GWB200_E_RUNTIME ("Max alignments must be at least 1."). alloc/release may be NULL (cudaMalloc / cudaFree). */
+int gwb200_global_aligner_create(gwb200_global_aligner** out, int32_t algorithm, int32_t max_query_length, int32_t max_target_length,
+                                 int32_t max_alignments, void* stream, int32_t device_id, gwb200_device_alloc_fn alloc,
+                                 gwb200_device_free_fn release, void* user);
+void gwb200_global_aligner_destroy(gwb200_global_aligner* aligner);
+/* AlignerGlobal::add_alignment (aligner_global.cpp:78-141): returns a gwb200_aligner_status */
+int gwb200_global_aligner_add_alignment(gwb200_global_aligner* aligner, const char* query, int32_t query_length, const char* target,
+                                        int32_t target_length, int32_t reverse_complement_query, int32_t reverse_complement_target);
+int gwb200_global_aligner_align_all(gwb200_global_aligner* aligner);      /* aligner_global.cpp:143-160 */
+int gwb200_global_aligner_sync_alignments(gwb200_global_aligner* aligner); /* aligner_global.cpp:162-190 */
+int32_t gwb200_global_aligner_num_alignments(const gwb200_global_aligner* aligner);
+/* Result i after sync: *length = number of alignment columns (0 with *has_result == 0: the alignment failed and the reference
+ * leaves its Alignment untouched); *is_optimal as AlignmentImpl::set_alignment receives it. */
+int gwb200_global_aligner_result_info(const gwb200_global_aligner* aligner, int32_t i, int32_t* has_result, int32_t* is_optimal, int32_t* length);
+/* The alignment columns of result i in forward order (gwb200_alignment_state bytes); states must hold *length entries. */
+int gwb200_global_aligner_result_states(const gwb200_global_aligner* aligner, int32_t i, int8_t* states);
+int gwb200_global_aligner_reset(gwb200_global_aligner* aligner);           /* aligner_global.cpp:192-195 */
+int64_t gwb200_global_aligner_last_cells(gwb200_global_aligner* aligner);
+float gwb200_global_aligner_last_kernel_ms(gwb200_global_aligner* aligner);
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic workloads: the reference's own generators
  * (common/base/include/claraparabricks/genomeworks/utils/genomeutils.hpp:33-142, std::minstd_rand).
  * ---------------------------------------------------------------------------------------------- */

@@ -15,6 +15,10 @@
 #include <claraparabricks/genomeworks/cudaaligner/cudaaligner.hpp>
 #include <claraparabricks/genomeworks/cudaaligner/aligner.hpp>
 #include <claraparabricks/genomeworks/cudaaligner/alignment.hpp>
+// the in-library aligners that no factory exposes (AlignerGlobalMyers, AlignerGlobalUkkonen): the reference's own class headers
+#include <aligner_global_myers.hpp>
+#include <aligner_global_ukkonen.hpp>
+#include <aligner_global_hirschberg_myers.hpp>
 
 #include <cuda_runtime_api.h>
 
@@ -260,6 +264,84 @@ int ref_aligner_run(int32_t n_pairs, const int32_t* q_len, const char* q_data, c
                 aligner->reset();
             }
             (void)done;
+        }
+        if (timings_ms)
+        {
+            timings_ms[0] = now_ms() - t_all0;
+            timings_ms[1] = t_proc;
+        }
+        cudaStreamDestroy(stream);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (errbuf && errbuf_len > 0)
+        {
+            std::strncpy(errbuf, e.what(), errbuf_len - 1);
+            errbuf[errbuf_len - 1] = 0;
+        }
+        return -1;
+    }
+}
+
+// Runs one of the reference's fixed-size global aligners over n_pairs pairs in one batch:
+//   algorithm 0: create_aligner(max_query, max_target, n_pairs, global_alignment, stream, 0) -- the deprecated factory
+//                (cudaaligner/src/aligner.cpp:31-74: AlignerGlobalHirschbergMyers)
+//   algorithm 1: AlignerGlobalMyers, 2: AlignerGlobalUkkonen (cudaaligner/src/aligner_global_{myers,ukkonen}.hpp)
+// Outputs as ref_aligner_run.
+int ref_global_aligner_run(int32_t n_pairs, const int32_t* q_len, const char* q_data, const int32_t* t_len, const char* t_data,
+                           int32_t algorithm, int32_t max_query_length, int32_t max_target_length, int32_t* status, int32_t* is_optimal,
+                           int32_t* edit_distance, char* cigar_basic, char* cigar_ext, int32_t cigar_stride, double* timings_ms, char* errbuf,
+                           int32_t errbuf_len)
+{
+    try
+    {
+        cudaaligner::Init();
+        cudaStream_t stream;
+        cudaStreamCreate(&stream);
+        const double t_all0 = now_ms();
+        double t_proc       = 0.;
+        {
+            std::unique_ptr<cudaaligner::Aligner> aligner;
+            if (algorithm == 0)
+            {
+                aligner = cudaaligner::create_aligner(max_query_length, max_target_length, n_pairs, cudaaligner::AlignmentType::global_alignment,
+                                                      stream, 0);
+            }
+            else
+            {
+                DefaultDeviceAllocator allocator = create_default_device_allocator(int64_t(8) << 30);
+                if (algorithm == 1)
+                    aligner.reset(new cudaaligner::AlignerGlobalMyers(max_query_length, max_target_length, n_pairs, allocator, stream, 0));
+                else
+                    aligner.reset(new cudaaligner::AlignerGlobalUkkonen(max_query_length, max_target_length, n_pairs, allocator, stream, 0));
+            }
+            int64_t qo = 0, to = 0;
+            for (int32_t i = 0; i < n_pairs; ++i)
+            {
+                cudaaligner::StatusType st = aligner->add_alignment(q_data + qo, q_len[i], t_data + to, t_len[i]);
+                if (st != cudaaligner::StatusType::success)
+                    throw std::runtime_error("reference add_alignment returned status " + std::to_string(static_cast<int>(st)));
+                qo += q_len[i];
+                to += t_len[i];
+            }
+            const double t0 = now_ms();
+            aligner->align_all();
+            aligner->sync_alignments();
+            t_proc += now_ms() - t0;
+            const auto& res = aligner->get_alignments();
+            for (int32_t p = 0; p < static_cast<int32_t>(res.size()); ++p)
+            {
+                status[p]        = static_cast<int32_t>(res[p]->get_status());
+                is_optimal[p]    = res[p]->is_optimal() ? 1 : 0;
+                edit_distance[p] = res[p]->get_edit_distance();
+                std::string cb   = res[p]->convert_to_cigar(cudaaligner::CigarFormat::basic);
+                std::string ce   = res[p]->convert_to_cigar(cudaaligner::CigarFormat::extended);
+                if (static_cast<int32_t>(cb.size()) >= cigar_stride || static_cast<int32_t>(ce.size()) >= cigar_stride)
+                    throw std::runtime_error("cigar_stride too small");
+                std::strcpy(cigar_basic + static_cast<int64_t>(p) * cigar_stride, cb.c_str());
+                std::strcpy(cigar_ext + static_cast<int64_t>(p) * cigar_stride, ce.c_str());
+            }
         }
         if (timings_ms)
         {

@@ -16,7 +16,7 @@ def lib():
     global _lib
     if _lib is None:
         path = os.path.join(_ORACLE_DIR, "liboracle.so")
-        srcs = [os.path.join(_ORACLE_DIR, f) for f in ("poa_oracle.cpp", "myers_oracle.cpp")]
+        srcs = [os.path.join(_ORACLE_DIR, f) for f in ("poa_oracle.cpp", "myers_oracle.cpp", "global_oracle.cpp")]
         if (not os.path.exists(path)) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
             subprocess.check_call(["make", "-C", _ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
         _lib = C.CDLL(path)
@@ -213,3 +213,42 @@ def myers_align(query, target, max_bandwidth, max_elements_per_matrix=0):
     a, r = actions[:k].copy(), runs[:k].copy()
     return dict(status=status.value, is_optimal=opt.value, actions=a, runs=r, cigar=cigar_from_runs(a, r),
                 cigar_extended=cigar_from_runs(a, r, True), edit_distance=edit_distance_from_runs(a, r), cells=cells.value)
+
+
+def states_to_cigar(states, extended=False):
+    """AlignmentImpl::convert_to_cigar (alignment_impl.cpp:99-153) for an expanded AlignmentState vector."""
+    sym = "=XID" if extended else "MMID"
+    out, prev, n = [], None, 0
+    for s in states:
+        c = sym[int(s)]
+        if c == prev:
+            n += 1
+        else:
+            if prev is not None:
+                out.append("%d%s" % (n, prev))
+            prev, n = c, 1
+    if prev is not None:
+        out.append("%d%s" % (n, prev))
+    return "".join(out)
+
+
+def hirschberg_myers_align(query, target, max_query_length=None):
+    """AlignerGlobalHirschbergMyers as create_aligner(max_query_length, ...) builds it -> (states ndarray, failed)."""
+    q = query.encode() if isinstance(query, str) else bytes(query)
+    t = target.encode() if isinstance(target, str) else bytes(target)
+    mq = len(q) if max_query_length is None else max_query_length
+    out = np.zeros(len(q) + len(t) + 1, dtype=np.int8)
+    failed = C.c_int32(0)
+    lib().oracle_hirschberg_myers_align.restype = C.c_int32
+    n = lib().oracle_hirschberg_myers_align(q, C.c_int32(len(q)), t, C.c_int32(len(t)), C.c_int32(mq), _p(out, C.c_int8), C.byref(failed))
+    return out[:n].copy(), bool(failed.value)
+
+
+def myers_full_align(query, target):
+    """AlignerGlobalMyers (unbanded) -> states ndarray."""
+    q = query.encode() if isinstance(query, str) else bytes(query)
+    t = target.encode() if isinstance(target, str) else bytes(target)
+    out = np.zeros(len(q) + len(t) + 1, dtype=np.int8)
+    lib().oracle_myers_full_align.restype = C.c_int32
+    n = lib().oracle_myers_full_align(q, C.c_int32(len(q)), t, C.c_int32(len(t)), _p(out, C.c_int8))
+    return out[:n].copy()

@@ -117,3 +117,29 @@ def spoa_consensus(win_nseq, seq_len, seq_data, n_threads=0, match=8, mismatch=-
                                      C.c_int32(gap), C.c_int32(n_threads), _p(buf), C.c_int32(stride), C.byref(cells))
     cons = [bytes(buf[i]).split(b"\0", 1)[0].decode() for i in range(n)] if want_strings else None
     return dict(seconds=secs, cells=cells.value, consensus=cons, threads=n_threads or spoa().spoa_hardware_threads())
+
+
+def ref_global_aligner_run(q_len, q_data, t_len, t_data, algorithm, max_query_length, max_target_length, cigar_stride=None):
+    """algorithm 0: the reference's deprecated factory (AlignerGlobalHirschbergMyers); 1: AlignerGlobalMyers; 2: AlignerGlobalUkkonen."""
+    q_len = np.ascontiguousarray(q_len, dtype=np.int32)
+    t_len = np.ascontiguousarray(t_len, dtype=np.int32)
+    q_data = np.ascontiguousarray(q_data, dtype=np.uint8)
+    t_data = np.ascontiguousarray(t_data, dtype=np.uint8)
+    n = len(q_len)
+    if cigar_stride is None:
+        cigar_stride = int(12 * (int(q_len.max(initial=1)) + int(t_len.max(initial=1))) + 64)
+    status = np.full(n, -99, dtype=np.int32)
+    opt = np.zeros(n, dtype=np.int32)
+    ed = np.zeros(n, dtype=np.int32)
+    cb = np.zeros((n, cigar_stride), dtype=np.uint8)
+    ce = np.zeros((n, cigar_stride), dtype=np.uint8)
+    timings = np.zeros(2, dtype=np.float64)
+    err = C.create_string_buffer(1024)
+    rc = gwref().ref_global_aligner_run(C.c_int32(n), _p(q_len), _p(q_data), _p(t_len), _p(t_data), C.c_int32(algorithm),
+                                        C.c_int32(max_query_length), C.c_int32(max_target_length), _p(status), _p(opt), _p(ed), _p(cb), _p(ce),
+                                        C.c_int32(cigar_stride), _p(timings), err, C.c_int32(1024))
+    if rc != 0:
+        raise RuntimeError("reference global aligner failed: " + err.value.decode())
+    return dict(status=status, is_optimal=opt, edit_distance=ed,
+                cigar_basic=[bytes(cb[i]).split(b"\0", 1)[0].decode() for i in range(n)],
+                cigar_extended=[bytes(ce[i]).split(b"\0", 1)[0].decode() for i in range(n)], timings=timings)
