@@ -592,6 +592,9 @@ struct gwb200_global_aligner
     DevBuf<int32_t> len_d, res_len_d, scores_d, leaf_sc_d;
     DevBuf<int8_t> res_d;
     DevBuf<galign::WordType> qpat_d, leaf_pv_d, leaf_mv_d, col_ws_d;
+    DevBuf<int16_t> ukk_scores_d;
+    int64_t ukk_matrix_elems = 0;
+    int32_t ukk_bw_max = 0, ukk_max_diff = 0;
     DevBuf<unsigned long long> cells_d;
     int32_t n          = 0; // alignments added
     int32_t n_launched = 0;
@@ -615,7 +618,7 @@ int gwb200_global_aligner_create(gwb200_global_aligner** out, int32_t algorithm,
         return set_error(GWB200_E_INVALID_ARGUMENT, "max_alignments must be non-negative.");
     if (max_alignments < 1)
         return set_error(GWB200_E_RUNTIME, "Max alignments must be at least 1.");
-    if (algorithm != GWB200_GLOBAL_HIRSCHBERG_MYERS && algorithm != GWB200_GLOBAL_MYERS)
+    if (algorithm != GWB200_GLOBAL_HIRSCHBERG_MYERS && algorithm != GWB200_GLOBAL_MYERS && algorithm != GWB200_GLOBAL_UKKONEN)
         return set_error(GWB200_E_INVALID_ARGUMENT, "unknown global alignment algorithm");
     DeviceGuard guard(device_id);
     auto* a            = new gwb200_global_aligner();
@@ -633,12 +636,21 @@ int gwb200_global_aligner_create(gwb200_global_aligner** out, int32_t algorithm,
     // unbanded Myers: the whole matrix (aligner_global_myers.cpp:32-38)
     a->leaf_elems = algorithm == GWB200_GLOBAL_MYERS ? static_cast<int64_t>(max_nw) * (max_target_length + 1) : static_cast<int64_t>(max_nw) * 64;
     a->leaf_elems = std::max<int64_t>(a->leaf_elems, 1);
+    if (algorithm == GWB200_GLOBAL_UKKONEN)
+    {
+        // aligner_global_ukkonen.cpp:30-45 (query has to be within 10 % of the target length, p = 100) and
+        // ukkonen_max_score_matrix_size (ukkonen_gpu.cu:327-338)
+        a->leaf_elems       = 1;
+        a->ukk_max_diff     = static_cast<int32_t>(static_cast<float>(max_target_length) * 0.1f);
+        a->ukk_bw_max       = (1 + a->ukk_max_diff + 2 * 100 + 1) / 2;
+        a->ukk_matrix_elems = static_cast<int64_t>(a->ukk_bw_max) * 2 * (static_cast<int64_t>(a->max_len) + 1);
+    }
     a->col_smem_words = std::min(max_nw + 1, 4096); // 2 x 16 KB of column state at most in shared memory
     a->hooks.alloc   = alloc;
     a->hooks.release = release;
     a->hooks.user    = user;
     a->seq_d.hooks = a->len_d.hooks = a->res_len_d.hooks = a->scores_d.hooks = a->leaf_sc_d.hooks = a->res_d.hooks = a->qpat_d.hooks =
-        a->leaf_pv_d.hooks = a->leaf_mv_d.hooks = a->col_ws_d.hooks = a->cells_d.hooks = &a->hooks;
+        a->leaf_pv_d.hooks = a->leaf_mv_d.hooks = a->col_ws_d.hooks = a->cells_d.hooks = a->ukk_scores_d.hooks = &a->hooks;
     const int64_t n = max_alignments;
     bool ok = a->seq_h.ensure(2ll * a->max_len * n + 16, false) && a->len_h.ensure(2 * n, false) && a->res_len_h.ensure(n, false) &&
               a->res_h.ensure(static_cast<int64_t>(a->max_result_length) * n + 16, false) && a->cells_h.ensure(1, false) &&
@@ -646,7 +658,7 @@ int gwb200_global_aligner_create(gwb200_global_aligner** out, int32_t algorithm,
               a->res_d.ensure(static_cast<int64_t>(a->max_result_length) * n + 16) && a->qpat_d.ensure(8ll * a->pat_stride * n) &&
               a->scores_d.ensure(2ll * (max_target_length + 1) * n) && a->leaf_pv_d.ensure(a->leaf_elems * n) &&
               a->leaf_mv_d.ensure(a->leaf_elems * n) && a->leaf_sc_d.ensure(a->leaf_elems * n) && a->col_ws_d.ensure(2ll * a->pat_stride * n) &&
-              a->cells_d.ensure(1);
+              a->cells_d.ensure(1) && (algorithm != GWB200_GLOBAL_UKKONEN || a->ukk_scores_d.ensure(a->ukk_matrix_elems * n));
     if (!ok)
     {
         gwb200_global_aligner_destroy(a);
@@ -675,6 +687,7 @@ void gwb200_global_aligner_destroy(gwb200_global_aligner* a)
     a->leaf_mv_d.release();
     a->col_ws_d.release();
     a->cells_d.release();
+    a->ukk_scores_d.release();
     a->seq_h.release();
     a->len_h.release();
     a->res_len_h.release();
@@ -696,6 +709,8 @@ int gwb200_global_aligner_add_alignment(gwb200_global_aligner* a, const char* qu
         return GWB200_ALN_GENERIC_ERROR;
     if (a->n >= a->max_alignments)
         return GWB200_ALN_EXCEEDED_MAX_ALIGNMENTS;
+    if (a->algorithm == GWB200_GLOBAL_UKKONEN && std::abs(query_length - target_length) > a->ukk_max_diff)
+        return GWB200_ALN_EXCEEDED_MAX_ALIGNMENT_DIFFERENCE; // aligner_global_ukkonen.cpp:52-60, checked before the base class
     if (query_length > a->max_query || target_length > a->max_target)
         return GWB200_ALN_EXCEEDED_MAX_LENGTH;
     static const char lookup[4] = {'T', 'G', 'A', 'C'}; // genomeutils::reverse_complement (utils/genomeutils.hpp:144-154)
@@ -749,7 +764,29 @@ int gwb200_global_aligner_align_all(gwb200_global_aligner* a)
     P.cells                = a->cells_d.p;
     const int32_t smem     = 2 * a->col_smem_words * static_cast<int32_t>(sizeof(galign::WordType));
     cudaEventRecord(a->ev0, a->stream);
-    galign::global_align_kernel<<<n, 32, smem, a->stream>>>(P);
+    if (a->algorithm == GWB200_GLOBAL_UKKONEN)
+    {
+        galign::UkkonenParams U{};
+        U.seqs              = a->seq_d.p;
+        U.seq_lengths       = a->len_d.p;
+        U.max_len           = a->max_len;
+        U.n_alignments      = n;
+        U.max_result_length = a->max_result_length;
+        U.results           = a->res_d.p;
+        U.result_lengths    = a->res_len_d.p;
+        U.scores            = a->ukk_scores_d.p;
+        U.matrix_elems      = a->ukk_matrix_elems;
+        U.p                 = 100; // ukkonen_p_, aligner_global_ukkonen.cpp:36
+        U.bw_capacity       = (a->ukk_bw_max + 7) / 8 * 8;
+        const int32_t threads = std::min(1024, (a->ukk_bw_max + 31) / 32 * 32);
+        const int32_t usmem   = 3 * U.bw_capacity * static_cast<int32_t>(sizeof(int16_t));
+        U.cells             = a->cells_d.p;
+        galign::ukkonen_align_kernel<<<n, threads, usmem, a->stream>>>(U);
+    }
+    else
+    {
+        galign::global_align_kernel<<<n, 32, smem, a->stream>>>(P);
+    }
     count_launch();
     cudaEventRecord(a->ev1, a->stream);
     GWB200_CUDA_TRY(cudaGetLastError());

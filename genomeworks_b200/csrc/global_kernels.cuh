@@ -475,5 +475,143 @@ __global__ void __launch_bounds__(32, 16) global_align_kernel(const GlobalParams
     }
 }
 
+
+// ---- AlignerGlobalUkkonen (cudaaligner/src/ukkonen_gpu.cu:62-262, aligner_global_ukkonen.cpp): banded unit-cost NW with the fixed
+// band parameter p = 100, int16 scores ("infinity" = 32766), in the reference's slot coordinates (k, l) = ((j - i + p) / 2, i + j)
+// because the slot layout is observable (boundary values in never-computed slots, truncating neighbour mapping in the backtrace).
+// This repo's shape: one CTA per alignment, one anti-diagonal l per barrier; the last two anti-diagonals live in shared memory, a
+// slot is written once (computed value or its initial value) as part of a contiguous int16 row of the band matrix, so the separate
+// initialisation pass of the reference (a second sweep over the whole matrix) does not exist.
+struct UkkonenParams
+{
+    const char* seqs;
+    const int32_t* seq_lengths;
+    int32_t max_len;
+    int32_t n_alignments;
+    int32_t max_result_length;
+    int8_t* results;
+    int32_t* result_lengths;
+    int16_t* scores;      // [n][matrix_elems]
+    int64_t matrix_elems; // ukkonen_max_score_matrix_size (ukkonen_gpu.cu:327-338)
+    int32_t p;
+    int32_t bw_capacity;  // slots per anti-diagonal the shared memory holds
+    unsigned long long* cells;
+};
+
+constexpr int32_t kUkkMax = 32766;
+
+__global__ void ukkonen_align_kernel(const UkkonenParams P)
+{
+    extern __shared__ int16_t s_diag[]; // [3][bw_capacity]
+    const int32_t a = blockIdx.x;
+    if (a >= P.n_alignments)
+        return;
+    int32_t m          = P.seq_lengths[2 * a] + 1;
+    int32_t n          = P.seq_lengths[2 * a + 1] + 1;
+    const char* query  = P.seqs + static_cast<int64_t>(2 * a) * P.max_len;
+    const char* target = P.seqs + static_cast<int64_t>(2 * a + 1) * P.max_len;
+    int8_t ins = myers::st_insertion, del = myers::st_deletion;
+    if (m > n)
+    {
+        const int32_t t = m;
+        m               = n;
+        n               = t;
+        const char* c   = query;
+        query           = target;
+        target          = c;
+        ins             = myers::st_deletion;
+        del             = myers::st_insertion;
+    }
+    const int32_t p         = P.p;
+    const int32_t bw        = (1 + n - m + 2 * p + 1) / 2;
+    const int32_t cols      = n + m;
+    const int32_t kmax_odd  = (n - m + 2 * p - 1) / 2 + 1;
+    const int32_t kmax_even = (n - m + 2 * p) / 2 + 1;
+    int16_t* const S        = P.scores + static_cast<int64_t>(a) * P.matrix_elems;
+    const int32_t cap       = P.bw_capacity;
+    for (int32_t l = 0; l < cols; l++)
+    {
+        int16_t* const cur      = s_diag + (l % 3) * cap;
+        const int16_t* const p1 = s_diag + ((l + 2) % 3) * cap;
+        const int16_t* const p2 = s_diag + ((l + 1) % 3) * cap;
+        const bool even_type    = ((l + p) & 1) == 0;
+        const int32_t kmax      = even_type ? kmax_even : kmax_odd;
+        for (int32_t k = threadIdx.x; k < bw; k += blockDim.x)
+        {
+            const int32_t j = k - (p + l) / 2 + l;
+            const int32_t i = l - j;
+            int32_t v       = (i == 0) ? j : (j == 0 ? i : kUkkMax);
+            if (k < kmax)
+            {
+                const int32_t dd   = even_type ? 2 * k : 2 * k + 1;
+                const int32_t lmin = abs(dd - p);
+                const int32_t lmax = dd <= p ? 2 * (m - p + dd) + lmin : 2 * min(m, n - dd + p) + lmin;
+                if (lmin + 1 <= l && l < lmax)
+                {
+                    const int32_t diag = l < 2 ? kUkkMax : p2[k] + (query[i - 1] == target[j - 1] ? 0 : 1);
+                    int32_t left, above;
+                    if (even_type)
+                    {
+                        left  = (k < 1 || l < 1) ? kUkkMax : p1[k - 1] + 1;
+                        above = l < 1 ? kUkkMax : p1[k] + 1;
+                    }
+                    else
+                    {
+                        left  = l < 1 ? kUkkMax : p1[k] + 1;
+                        above = (l < 1 || k + 1 >= bw) ? kUkkMax : p1[k + 1] + 1;
+                    }
+                    v = min(static_cast<int32_t>(static_cast<int16_t>(diag)),
+                            min(static_cast<int32_t>(static_cast<int16_t>(left)), static_cast<int32_t>(static_cast<int16_t>(above))));
+                }
+            }
+            cur[k]                             = static_cast<int16_t>(v);
+            S[k + static_cast<int64_t>(bw) * l] = static_cast<int16_t>(v);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        auto get = [&](int32_t i, int32_t j) -> int32_t {
+            const int32_t k = (j - i + p) / 2; // truncates towards zero (to_band_indices, ukkonen_gpu.cu:54-59)
+            const int32_t l = j + i;
+            return (k < 0 || k >= bw || l < 0 || l >= cols) ? kUkkMax : S[k + static_cast<int64_t>(bw) * l];
+        };
+        int8_t* const path = P.results + static_cast<int64_t>(a) * P.max_result_length;
+        int32_t i = m - 1, j = n - 1, pos = 0;
+        int32_t my = get(i, j);
+        while (i > 0 && j > 0)
+        {
+            const int32_t above = get(i - 1, j), diag = get(i - 1, j - 1), left = get(i, j - 1);
+            int8_t r;
+            if (left + 1 == my)
+            {
+                r  = ins;
+                my = left;
+                --j;
+            }
+            else if (above + 1 == my)
+            {
+                r  = del;
+                my = above;
+                --i;
+            }
+            else
+            {
+                r  = (diag == my) ? myers::st_match : myers::st_mismatch;
+                my = diag;
+                --i;
+                --j;
+            }
+            path[pos++] = r;
+        }
+        for (; i > 0; --i)
+            path[pos++] = del;
+        for (; j > 0; --j)
+            path[pos++] = ins;
+        P.result_lengths[a] = pos;
+        atomicAdd(P.cells, static_cast<unsigned long long>(bw) * static_cast<unsigned long long>(cols));
+    }
+}
+
 } // namespace galign
 } // namespace gwb200

@@ -10,6 +10,7 @@
 #include "poa_kernels_v2.cuh"
 #include "poa_kernels_v3.cuh"
 
+#include <atomic>
 #include <cstdlib>
 
 #include <algorithm>
@@ -64,6 +65,7 @@ struct gwb200_poa_batch
     gwb200_poa_config cfg{};
     int32_t gap = -8, mismatch = -6, match = 8;
     bool score32 = false, size32 = false, msa = false;
+    bool accurate = false; // SPOA_ACCURATE semantics (racon sort after every read)
     int32_t score_bytes = 2, size_bytes = 2;
     int32_t bid = 0;
 
@@ -131,13 +133,28 @@ struct Sizes
     int32_t aln_capacity = 0, stack_capacity = 0;
 };
 
+// SPOA_ACCURATE as a library-wide switch (the reference makes it a build flag, cudapoa_kernels.cuh:508-520): batches created while
+// it is on re-sort their graphs with racon's topological sort after every read
+std::atomic<int> g_spoa_accurate{-1};
+bool spoa_accurate()
+{
+    int v = g_spoa_accurate.load();
+    if (v < 0)
+    {
+        const char* e = std::getenv("GWB200_SPOA_ACCURATE");
+        v             = (e && std::atoi(e) != 0) ? 1 : 0;
+    }
+    return v != 0;
+}
+
 Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz, bool msa, bool tb = false, int32_t trace_bytes = 2)
 {
     Sizes s;
     const int64_t mn = c.max_nodes_per_graph;
     const int64_t E  = kMaxEdges;
     s.aln_capacity   = c.max_nodes_per_graph + c.max_sequence_size + 16;
-    s.stack_capacity = msa ? 4 * c.max_nodes_per_graph + 16 : 0;
+    const bool accurate = spoa_accurate();
+    s.stack_capacity = (msa || accurate) ? 4 * c.max_nodes_per_graph + 16 : 0;
     s.seq_bytes_per_poa = static_cast<int64_t>(c.max_sequences_per_poa) * align_up(std::max(c.max_sequence_size, 1), 4);
     int64_t d = 0;
     d += mn * 1;                 // nodes
@@ -159,6 +176,10 @@ Sizes compute_sizes(const gwb200_poa_config& c, int32_t score_bytes, int32_t sz,
         d += mn * sz + mn * 2;         // msa_col, marks, check
         d += static_cast<int64_t>(s.stack_capacity) * sz;
         d += static_cast<int64_t>(c.max_sequences_per_poa) * c.max_consensus_size;
+    }
+    else if (accurate)
+    {
+        d += mn * 2 + static_cast<int64_t>(s.stack_capacity) * sz; // marks, check, stack of the racon sort
     }
     d += (mn + 1) * 16;                                   // v2 row metadata
     d += (align_up(std::max(c.max_sequence_size, 1), 4) + 8ll) * sz; // v2 read -> node map
@@ -546,6 +567,10 @@ int gwb200_poa_decode_error(int32_t status, char* message, int32_t message_len, 
     return 0;
 }
 
+/* Library-wide SPOA_ACCURATE switch (cudapoa_kernels.cuh:508-520 makes it a build flag): affects batches created afterwards. */
+void gwb200_poa_set_spoa_accurate(int32_t on) { g_spoa_accurate.store(on ? 1 : 0); }
+int32_t gwb200_poa_get_spoa_accurate(void) { return spoa_accurate() ? 1 : 0; }
+
 int64_t gwb200_poa_estimate_max_poas(const gwb200_poa_config* cfg, int32_t msa_flag, float gpu_memory_usage_quota, int16_t mismatch_score,
                                      int16_t gap_score, int16_t match_score)
 {
@@ -623,6 +648,7 @@ static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void
     b->score_bytes      = b->score32 ? 4 : 2;
     b->size_bytes       = b->size32 ? 4 : 2;
     b->msa              = (output_mask & GWB200_POA_OUTPUT_MSA) != 0;
+    b->accurate         = spoa_accurate();
     b->tb_mode          = cfg->band_mode == GWB200_POA_STATIC_BAND_TRACEBACK || cfg->band_mode == GWB200_POA_ADAPTIVE_BAND_TRACEBACK;
     b->trace_bytes      = cfg->max_banded_pred_distance > INT8_MAX ? 2 : 1;
     if (b->tb_mode && cfg->max_banded_pred_distance < 1)
@@ -754,6 +780,13 @@ static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void
             P.stack_capacity = sz.stack_capacity;
             P.msa_out        = dc.take<uint8_t>(n * cfg->max_sequences_per_poa * mc);
         }
+        else if (b->accurate)
+        {
+            P.marks          = dc.take<uint8_t>(n * mn);
+            P.check          = dc.take<uint8_t>(n * mn);
+            P.stack          = dc.take<uint8_t>(n * sz.stack_capacity * S);
+            P.stack_capacity = sz.stack_capacity;
+        }
         b->X.row_meta    = dc.take<int4>(n * (mn + 1));
         b->X.rd_capacity = align_up(std::max(cfg->max_sequence_size, 1), 4) + 8;
         b->X.rd_node     = dc.take<uint8_t>(n * static_cast<int64_t>(b->X.rd_capacity) * S);
@@ -788,6 +821,7 @@ static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void
         P.mismatch             = b->mismatch;
         P.match                = b->match;
         P.msa                  = b->msa ? 1 : 0;
+        P.accurate             = b->accurate ? 1 : 0;
         P.aln_capacity         = sz.aln_capacity;
     }
     cudaEventCreate(&b->ev0);

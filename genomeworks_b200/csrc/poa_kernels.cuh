@@ -78,6 +78,7 @@ struct DeviceParams
     int32_t band_mode;
     int32_t gap, mismatch, match;
     int32_t msa;
+    int32_t accurate;     // SPOA_ACCURATE (cudapoa_kernels.cuh:508-520): racon's topological sort after every read
     int32_t aln_capacity; // entries in aln_graph / aln_read per window
     // per-window graph state; element (w, i) of an array with per-window extent E lives at base + w*E + i
     uint8_t* nodes;          // [max_nodes]
@@ -1314,7 +1315,11 @@ __global__ void __launch_bounds__(32, 16) poa_window_kernel(const DeviceParams P
             else
             {
                 node_count = nc;
-                topsort(g, node_count);
+                if (P.accurate)
+                    racon_topsort(g, node_count, P.marks + w * mn, P.check + w * mn,
+                                  static_cast<SizeT*>(P.stack) + static_cast<int64_t>(w) * P.stack_capacity, P.stack_capacity);
+                else
+                    topsort(g, node_count);
             }
         }
         __syncwarp();

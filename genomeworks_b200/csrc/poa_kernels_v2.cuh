@@ -1325,7 +1325,19 @@ __global__ void __launch_bounds__(32 * NW, (NW == 4 ? GWB200_POA_NW4_BLOCKS : (N
                 int32_t e  = add_alignment_v2<SizeT>(g, nc, alen, aln_graph, sequence, seq_len, aln_read, base_weights, path, rd_node);
                 GWB200_TIMER_LAP(3);
                 if (!e)
-                    topsort_v2<SizeT>(g, nc, pool, X.pool_bytes, static_cast<SizeT*>(P.cons_preds) + w * mn);
+                {
+                    if (P.accurate)
+                    {
+                        if ((threadIdx.x & 31) == 0)
+                            racon_topsort(g, nc, P.marks + w * mn, P.check + w * mn,
+                                          static_cast<SizeT*>(P.stack) + static_cast<int64_t>(w) * P.stack_capacity, P.stack_capacity);
+                        __syncwarp();
+                    }
+                    else
+                    {
+                        topsort_v2<SizeT>(g, nc, pool, X.pool_bytes, static_cast<SizeT*>(P.cons_preds) + w * mn);
+                    }
+                }
                 GWB200_TIMER_LAP(4);
                 if (lane == 0)
                 {

@@ -222,8 +222,8 @@ struct RowCtx
 // NJ consecutive chunks of one row, starting at chunk c0 (all of them exist: c0 + NJ <= number of chunks). Straight-line code:
 // every load of the group is issued before the first dependent instruction needs it. cin: carry into the first chunk (closed
 // value of the cell left of it), cleft: what is stored in that cell's place; both are updated for the next group.
-template <typename ScoreT, int32_t NJ>
-__device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int32_t c0, const int32_t lane, int32_t& cin, int32_t& cleft, const bool TWO)
+template <typename ScoreT, int32_t NJ, bool TWO>
+__device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int32_t c0, const int32_t lane, int32_t& cin, int32_t& cleft)
 {
     constexpr int32_t kMin = min_score_of<ScoreT>();
     constexpr int32_t CPL  = V3Cells<ScoreT>::kCPL;
@@ -236,8 +236,8 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
     {
         // ---- loads: read characters and the predecessors' units of every chunk
         uint32_t w[NJ][CPL / 4];
-        int32_t b0[NJ][CPL + 1], b1[NJ][CPL + 1];
-        bool in0[NJ], in1[NJ];
+        int32_t b0[NJ][CPL + 1], b1[TWO ? NJ : 1][CPL + 1];
+        bool in0[NJ], in1[TWO ? NJ : 1];
 #pragma unroll
         for (int32_t j = 0; j < NJ; j++)
         {
@@ -532,18 +532,29 @@ __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const
                 cx.gap   = gap;
                 cx.match = match;
                 cx.mismatch = mismatch;
-                // group sizes 4, 2, 1 only (one instantiation each, the second predecessor is a run-time flag): what the row loop
-                // executes has to stay resident in the instruction cache with 10+ windows per SM at different places
-                const bool two = pc == 2;
-                int32_t c0     = 0;
-                if (GC >= 4 && max_group >= 4)
-                    for (; c0 + 4 <= nchunks; c0 += 4)
-                        row_group_v3<ScoreT, (GC >= 4 ? 4 : 1)>(cx, c0, lane, cin, cleft, two);
-                if (max_group >= 2)
-                    for (; c0 + 2 <= nchunks; c0 += 2)
-                        row_group_v3<ScoreT, 2>(cx, c0, lane, cin, cleft, two);
-                for (; c0 < nchunks; c0++)
-                    row_group_v3<ScoreT, 1>(cx, c0, lane, cin, cleft, two);
+                // Few, compact instantiations run as loops: what the row loop executes has to stay resident in the instruction
+                // caches with 10+ windows per SM at different places of it. Measured on C3 (1480 windows, profiles/r02_summary.md):
+                // groups of 2 chunks 1121 windows/s, of 1 chunk 1012, of 4 chunks 962 (the fully unrolled 8-variant version 828)
+                int32_t c0 = 0;
+                if (pc == 2)
+                {
+                    if (max_group >= 2)
+                        for (; c0 + 2 <= nchunks; c0 += 2)
+                            row_group_v3<ScoreT, 2, true>(cx, c0, lane, cin, cleft);
+                    for (; c0 < nchunks; c0++)
+                        row_group_v3<ScoreT, 1, true>(cx, c0, lane, cin, cleft);
+                }
+                else
+                {
+                    if (GC >= 4 && max_group >= 4)
+                        for (; c0 + 4 <= nchunks; c0 += 4)
+                            row_group_v3<ScoreT, (GC >= 4 ? 4 : 1), false>(cx, c0, lane, cin, cleft);
+                    if (max_group >= 2)
+                        for (; c0 + 2 <= nchunks; c0 += 2)
+                            row_group_v3<ScoreT, 2, false>(cx, c0, lane, cin, cleft);
+                    for (; c0 < nchunks; c0++)
+                        row_group_v3<ScoreT, 1, false>(cx, c0, lane, cin, cleft);
+                }
             }
             else
             {
@@ -1810,7 +1821,19 @@ __device__ void process_window_v3(const DeviceParams& P, const V2Extra& X, const
                 error      = add_alignment_v2<SizeT>(g, nc, alen, aln_graph, sequence, seq_len, aln_read, base_weights, path, rd_node);
                 GWB200_TIMER_LAP(3);
                 if (!error)
-                    topsort_v3<SizeT>(g, nc, pool, X.pool_bytes, row_meta); // row_meta is free between traceback and the next rows
+                {
+                    if (P.accurate)
+                    {
+                        if (lane == 0)
+                            racon_topsort(g, nc, P.marks + w * mn, P.check + w * mn,
+                                          static_cast<SizeT*>(P.stack) + static_cast<int64_t>(w) * P.stack_capacity, P.stack_capacity);
+                        __syncwarp();
+                    }
+                    else
+                    {
+                        topsort_v3<SizeT>(g, nc, pool, X.pool_bytes, row_meta); // row_meta is free between traceback and the next rows
+                    }
+                }
                 GWB200_TIMER_LAP(4);
                 node_count = nc;
                 if (error)

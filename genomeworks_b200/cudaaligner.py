@@ -224,7 +224,7 @@ class GlobalAligner:
     max_alignments, ...) (aligner.hpp:183,196 -> AlignerGlobalHirschbergMyers, cudaaligner/src/aligner.cpp:31-74) and the in-library
     unbanded AlignerGlobalMyers. Host semantics = AlignerGlobal (cudaaligner/src/aligner_global.cpp:50-197)."""
 
-    ALGORITHMS = {"hirschberg_myers": 0, "myers": 1}
+    ALGORITHMS = {"hirschberg_myers": 0, "myers": 1, "ukkonen": 2}
 
     def __init__(self, max_query_length, max_target_length, max_alignments, algorithm="hirschberg_myers", stream=None, device_id=0):
         self._h = C.c_void_p()

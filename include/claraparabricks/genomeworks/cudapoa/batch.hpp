@@ -113,6 +113,9 @@ public:
               int16_t mismatch_score, int16_t match_score)
         : cfg_(cfg)
     {
+#ifdef SPOA_ACCURATE
+        gwb200_poa_set_spoa_accurate(1); // the reference's build flag (cudapoa_kernels.cuh:508-520)
+#endif
         const gwb200_poa_config c = cfg.to_c();
         check(gwb200_poa_batch_create(&h_, device_id, stream, max_gpu_mem, output_mask, &c, gap_score, mismatch_score, match_score));
     }
@@ -124,6 +127,9 @@ public:
         , allocator_(allocator)
         , block_bytes_(block_bytes)
     {
+#ifdef SPOA_ACCURATE
+        gwb200_poa_set_spoa_accurate(1); // the reference's build flag (cudapoa_kernels.cuh:508-520)
+#endif
         const gwb200_poa_config c = cfg.to_c();
         block_                    = allocator_.allocate(static_cast<std::size_t>(block_bytes_), {stream});
         try

@@ -75,6 +75,31 @@ inline T align(const T& value)
     {                                                                                   \
         claraparabricks::genomeworks::cudautils::gpu_assert((ans), __FILE__, __LINE__); \
     }
+// GW_NVTX_RANGE (reference cudautils.hpp:155-184): a scoped NVTX range when the including build defines GW_PROFILING (the
+// header-only NVTX v3 that ships with the CUDA toolkit: no extra library to link), otherwise nothing.
+#if defined(GW_PROFILING) && defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+namespace claraparabricks
+{
+namespace genomeworks
+{
+namespace cudautils
+{
+class nvtx_range
+{
+public:
+    explicit nvtx_range(char const* name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+    nvtx_range(const nvtx_range&) = delete;
+    nvtx_range& operator=(const nvtx_range&) = delete;
+};
+} // namespace cudautils
+} // namespace genomeworks
+} // namespace claraparabricks
+#define GW_NVTX_RANGE(varname, label) ::claraparabricks::genomeworks::cudautils::nvtx_range varname(label)
+#endif
+#endif
 #ifndef GW_NVTX_RANGE
 #define GW_NVTX_RANGE(varname, label)
 #endif

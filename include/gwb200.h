@@ -104,6 +104,13 @@ int gwb200_poa_init(void);
 /* cudapoa::decode_error(), cudapoa.hpp:55 -- writes NUL-terminated strings; unknown status -> GWB200_E_RUNTIME */
 int gwb200_poa_decode_error(int32_t status, char* message, int32_t message_len, char* hint, int32_t hint_len);
 
+/* SPOA_ACCURATE (cudapoa/src/cudapoa_kernels.cuh:508-530: a build flag of the reference that swaps the per-read topological sort
+ * for racon's, which makes the graphs -- and MSAs -- identical to 3rdparty/spoa's). Here a library-wide run-time switch, also settable
+ * with the environment variable GWB200_SPOA_ACCURATE=1 before the first batch; it applies to batches created afterwards. The C++
+ * headers turn it on when the including translation unit defines SPOA_ACCURATE. */
+void gwb200_poa_set_spoa_accurate(int32_t on);
+int32_t gwb200_poa_get_spoa_accurate(void);
+
 /* BatchBlock::estimate_max_poas(batch_size, msa_flag, memory_usage_quota, mismatch, gap, match) -- allocate_block.hpp:403-449:
  * how many windows of this configuration one batch holds when it may use `gpu_memory_usage_quota` of the currently free memory
  * of the current device (this engine's own arena layout). Used by get_multi_batch_sizes (utils.hpp:55-68). < 0 on error. */
@@ -263,14 +270,16 @@ float gwb200_aligner_last_kernel_ms(gwb200_aligner* aligner);
 /* ------------------------------------------------------------------------------------------------
  * cudaaligner, fixed-size global aligners: what the deprecated factory create_aligner(max_query_length, max_target_length,
  * max_alignments, type, [allocator,] stream, device) builds (cudaaligner/include/.../aligner.hpp:183,196; src/aligner.cpp:31-74
- * -> AlignerGlobalHirschbergMyers) and the in-library AlignerGlobalMyers (cudaaligner/src/aligner_global_myers.cpp).
+ * -> AlignerGlobalHirschbergMyers) and the in-library AlignerGlobalMyers / AlignerGlobalUkkonen (cudaaligner/src/aligner_global_{myers,
+ * ukkonen}.cpp).
  * Host behaviour = AlignerGlobal (cudaaligner/src/aligner_global.cpp:50-197): fixed-stride sequence and result slots,
  * results as one AlignmentState byte per alignment column in forward order.
  * ---------------------------------------------------------------------------------------------- */
 enum gwb200_global_algorithm
 {
     GWB200_GLOBAL_HIRSCHBERG_MYERS = 0, /* aligner_global_hirschberg_myers.cpp:32-75, hirschberg_myers_gpu.cu:575-699 */
-    GWB200_GLOBAL_MYERS            = 1  /* aligner_global_myers.cpp:40-70, myers_gpu.cu:256-442,1117-1139 */
+    GWB200_GLOBAL_MYERS            = 1, /* aligner_global_myers.cpp:40-70, myers_gpu.cu:256-442,1117-1139 */
+    GWB200_GLOBAL_UKKONEN          = 2  /* aligner_global_ukkonen.cpp:30-81, ukkonen_gpu.cu:62-262 (band p = 100, int16 scores) */
 };
 typedef struct gwb200_global_aligner gwb200_global_aligner; /* opaque: one cudaaligner::AlignerGlobal */
 

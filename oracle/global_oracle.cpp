@@ -11,8 +11,9 @@
 //       diagonal), aligner_global_hirschberg_myers.cpp:32-48 (workspace = ceil(max_query / 32) * 64 words), aligner_global.cpp:
 //       162-190 (the host reverses the path; a negative length would mean "not optimal", length 0 = failed).
 //   AlignerGlobalMyers            cudaaligner/src/myers_gpu.cu:370-442 (full matrix + the same backtrace).
-//   AlignerGlobalUkkonen          cudaaligner/src/ukkonen_gpu.cu:154-262 + ukkonen_cpu.cpp:103-263 (banded NW with doubling band,
-//       backtrace preference diagonal-first, see ukkonen_backtrace below).
+//   AlignerGlobalUkkonen          cudaaligner/src/ukkonen_gpu.cu:62-262 (banded unit-cost NW in slot coordinates, fixed p = 100,
+//       int16 scores, backtrace preference insertion, deletion, diagonal; query / target swapped when the query is longer),
+//       aligner_global_ukkonen.cpp:30-81.
 // Pinned against: the CIGAR tables of Test_AlignerGlobal.cpp:78-147 and test_cudaaligner_bindings.py (tests/test_oracle_global.py)
 // and, on the GPU box, the unmodified reference classes through oracle/_ref (tests/test_gpu_global_aligners.py).
 #include <algorithm>
@@ -219,6 +220,108 @@ bool hirschberg(const char* query, int32_t query_length, const char* target, int
     return true;
 }
 
+
+// ---- AlignerGlobalUkkonen (cudaaligner/src/ukkonen_gpu.cu:154-262 + the backtrace kernel :62-152, aligner_global_ukkonen.cpp) --------
+// The band lives in slot coordinates (k, l) = ((j - i + p) / 2, i + j), int16 scores, "infinity" = 32766. Restated slot by slot
+// because two details of that layout are observable: every slot whose (i, j) has i == 0 or j == 0 starts as a boundary value -- also
+// slots of diagonals beyond the band that a top-diagonal cell reads as its "above" neighbour -- and the backtrace maps neighbours
+// with a division that truncates towards zero.
+constexpr int32_t kUkkMax = 32766;
+
+int32_t ukkonen(const char* query_in, int32_t query_length, const char* target_in, int32_t target_length, int32_t p, std::vector<int8_t>& path)
+{
+    int32_t m = query_length + 1, n = target_length + 1;
+    const char* query  = query_in;
+    const char* target = target_in;
+    int8_t ins = st_insertion, del = st_deletion;
+    if (m > n)
+    {
+        std::swap(m, n);
+        std::swap(query, target);
+        std::swap(ins, del);
+    }
+    const int32_t bw        = (1 + n - m + 2 * p + 1) / 2;
+    const int32_t cols      = n + m;
+    const int32_t kmax_odd  = (n - m + 2 * p - 1) / 2 + 1;
+    const int32_t kmax_even = (n - m + 2 * p) / 2 + 1;
+    std::vector<int16_t> S(static_cast<size_t>(bw) * cols);
+    auto at = [&](int32_t k, int32_t l) -> int16_t& { return S[static_cast<size_t>(k) + static_cast<size_t>(bw) * l]; };
+    for (int32_t k = 0; k < bw; k++)
+        for (int32_t l = 0; l < cols; l++)
+        {
+            const int32_t j = k - (p + l) / 2 + l;
+            const int32_t i = l - j;
+            at(k, l)        = static_cast<int16_t>(i == 0 ? j : (j == 0 ? i : kUkkMax));
+        }
+    for (int32_t l = 0; l < cols; l++)
+    {
+        const bool even_type = ((l + p) % 2) == 0; // cells of this anti-diagonal sit on diagonals 2k - p (even type) or 2k + 1 - p
+        const int32_t kmax   = even_type ? kmax_even : kmax_odd;
+        for (int32_t k = 0; k < kmax && k < bw; k++)
+        {
+            const int32_t dd   = even_type ? 2 * k : 2 * k + 1;
+            const int32_t lmin = std::abs(dd - p);
+            const int32_t lmax = dd <= p ? 2 * (m - p + dd) + lmin : 2 * std::min(m, n - dd + p) + lmin;
+            if (!(lmin + 1 <= l && l < lmax))
+                continue;
+            const int32_t j = k - (p + l) / 2 + l;
+            const int32_t i = l - j;
+            int32_t diag = l - 2 < 0 ? kUkkMax : at(k, l - 2) + (query[i - 1] == target[j - 1] ? 0 : 1);
+            int32_t left, above;
+            if (even_type)
+            {
+                left  = (k - 1 < 0 || l - 1 < 0) ? kUkkMax : at(k - 1, l - 1) + 1;
+                above = l - 1 < 0 ? kUkkMax : at(k, l - 1) + 1;
+            }
+            else
+            {
+                left  = l - 1 < 0 ? kUkkMax : at(k, l - 1) + 1;
+                above = (l - 1 < 0 || k + 1 >= bw) ? kUkkMax : at(k + 1, l - 1) + 1;
+            }
+            at(k, l) = static_cast<int16_t>(std::min(static_cast<int16_t>(diag), std::min(static_cast<int16_t>(left), static_cast<int16_t>(above))));
+        }
+    }
+    auto band = [&](int32_t i, int32_t j, int32_t& k, int32_t& l) {
+        k = (j - i + p) / 2; // truncates towards zero, as the reference's to_band_indices
+        l = j + i;
+    };
+    auto get = [&](int32_t i, int32_t j) -> int32_t {
+        int32_t k, l;
+        band(i, j, k, l);
+        return (k < 0 || k >= bw || l < 0 || l >= cols) ? kUkkMax : at(k, l);
+    };
+    int32_t i = m - 1, j = n - 1;
+    int32_t my = get(i, j);
+    while (i > 0 && j > 0)
+    {
+        const int32_t above = get(i - 1, j), diag = get(i - 1, j - 1), left = get(i, j - 1);
+        if (left + 1 == my)
+        {
+            path.push_back(ins);
+            my = left;
+            --j;
+        }
+        else if (above + 1 == my)
+        {
+            path.push_back(del);
+            my = above;
+            --i;
+        }
+        else
+        {
+            path.push_back(diag == my ? st_match : st_mismatch);
+            my = diag;
+            --i;
+            --j;
+        }
+    }
+    for (; i > 0; --i)
+        path.push_back(del);
+    for (; j > 0; --j)
+        path.push_back(ins);
+    return static_cast<int32_t>(path.size());
+}
+
 } // namespace
 
 extern "C" {
@@ -250,6 +353,16 @@ int32_t oracle_myers_full_align(const char* query, int32_t query_length, const c
         path.insert(path.end(), query_length, st_deletion);
     else
         full_matrix_path(query, query_length, target, target_length, path);
+    std::reverse(path.begin(), path.end());
+    std::memcpy(actions, path.data(), path.size());
+    return static_cast<int32_t>(path.size());
+}
+
+// AlignerGlobalUkkonen with its fixed p = 100 (aligner_global_ukkonen.cpp:36). Returns the path length (forward order in actions).
+int32_t oracle_ukkonen_align(const char* query, int32_t query_length, const char* target, int32_t target_length, int32_t p, int8_t* actions)
+{
+    std::vector<int8_t> path;
+    ukkonen(query, query_length, target, target_length, p, path);
     std::reverse(path.begin(), path.end());
     std::memcpy(actions, path.data(), path.size());
     return static_cast<int32_t>(path.size());

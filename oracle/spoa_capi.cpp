@@ -92,6 +92,34 @@ double spoa_consensus_run(int32_t n_windows, const int32_t* win_nseq, const int3
     return secs;
 }
 
+// Multiple sequence alignment of ONE window (the pattern of cudapoa/tests/Test_CudapoaGenerateMSA2.cu:60-79): rows are written
+// NUL-terminated into msa[n_seqs * stride]. Returns the MSA width, -1 when stride is too small.
+int32_t spoa_msa_run(int32_t n_seqs, const int32_t* seq_len, const char* seq_data, int32_t match, int32_t mismatch, int32_t gap, char* msa,
+                     int32_t stride)
+{
+    auto engine = spoa::createAlignmentEngine(spoa::AlignmentType::kNW, static_cast<int8_t>(match), static_cast<int8_t>(mismatch), static_cast<int8_t>(gap));
+    auto graph  = spoa::createGraph();
+    int64_t off = 0;
+    for (int32_t s = 0; s < n_seqs; ++s)
+    {
+        std::string seq(seq_data + off, static_cast<size_t>(seq_len[s]));
+        off += seq_len[s];
+        auto alignment = engine->align(seq, graph);
+        graph->add_alignment(alignment, seq);
+    }
+    std::vector<std::string> rows;
+    graph->generate_multiple_sequence_alignment(rows);
+    int32_t width = 0;
+    for (int32_t s = 0; s < static_cast<int32_t>(rows.size()); ++s)
+    {
+        if (static_cast<int32_t>(rows[s].size()) >= stride)
+            return -1;
+        std::strcpy(msa + static_cast<int64_t>(s) * stride, rows[s].c_str());
+        width = static_cast<int32_t>(rows[s].size());
+    }
+    return width;
+}
+
 // ---- streaming interface: FULL windows at a bounded cost per step ----------------------------------------------------------
 // One window of the long-read workload costs spoa minutes per core, far more than a benchmark step may take. A stream keeps one
 // window in progress per host thread and every step() call fuses the next `reads_per_step` reads of every thread's window (a

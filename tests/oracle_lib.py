@@ -252,3 +252,13 @@ def myers_full_align(query, target):
     lib().oracle_myers_full_align.restype = C.c_int32
     n = lib().oracle_myers_full_align(q, C.c_int32(len(q)), t, C.c_int32(len(t)), _p(out, C.c_int8))
     return out[:n].copy()
+
+
+def ukkonen_align(query, target, p=100):
+    """AlignerGlobalUkkonen (fixed p = 100) -> states ndarray."""
+    q = query.encode() if isinstance(query, str) else bytes(query)
+    t = target.encode() if isinstance(target, str) else bytes(target)
+    out = np.zeros(len(q) + len(t) + 1, dtype=np.int8)
+    lib().oracle_ukkonen_align.restype = C.c_int32
+    n = lib().oracle_ukkonen_align(q, C.c_int32(len(q)), t, C.c_int32(len(t)), C.c_int32(p), _p(out, C.c_int8))
+    return out[:n].copy()

@@ -143,3 +143,15 @@ def ref_global_aligner_run(q_len, q_data, t_len, t_data, algorithm, max_query_le
     return dict(status=status, is_optimal=opt, edit_distance=ed,
                 cigar_basic=[bytes(cb[i]).split(b"\0", 1)[0].decode() for i in range(n)],
                 cigar_extended=[bytes(ce[i]).split(b"\0", 1)[0].decode() for i in range(n)], timings=timings)
+
+
+def spoa_msa(seqs, match=8, mismatch=-6, gap=-8, stride=8192):
+    """3rdparty/spoa MSA of one window (list of str) -> list of rows."""
+    lens = np.array([len(x) for x in seqs], dtype=np.int32)
+    data = np.frombuffer(("".join(seqs) + "\0").encode(), dtype=np.uint8)
+    out = np.zeros((len(seqs), stride), dtype=np.uint8)
+    w = spoa().spoa_msa_run(C.c_int32(len(seqs)), _p(lens), _p(data), C.c_int32(match), C.c_int32(mismatch), C.c_int32(gap), _p(out),
+                            C.c_int32(stride))
+    if w < 0:
+        raise RuntimeError("stride too small")
+    return [bytes(out[i]).split(b"\0", 1)[0].decode() for i in range(len(seqs))]

@@ -40,10 +40,12 @@ def run_ours(pairs, algorithm, max_q=None, max_t=None):
     return res
 
 
-@pytest.mark.parametrize("algorithm", ["hirschberg_myers", "myers"])
+@pytest.mark.parametrize("algorithm", ["hirschberg_myers", "myers", "ukkonen"])
 def test_reference_kat_table(algorithm):
-    res = run_ours([(q, t) for q, t, _, _ in KAT], algorithm)
-    for a, (q, t, cigar, dist) in zip(res, KAT):
+    # Ukkonen cannot handle empty sequences (Test_AlignerGlobal.cpp:151-152)
+    kat = [k for k in KAT if (k[0] and k[1]) or algorithm != "ukkonen"]
+    res = run_ours([(q, t) for q, t, _, _ in kat], algorithm, max_q=64, max_t=64)
+    for a, (q, t, cigar, dist) in zip(res, kat):
         assert a.status == cudaaligner.success and a.is_optimal
         assert a.convert_to_cigar() == cigar and a.get_edit_distance() == dist, (q, t, a.convert_to_cigar())
 
@@ -96,13 +98,17 @@ def test_admission_and_reset():
         cudaaligner.GlobalAligner(5, 5, 0)
 
 
-@pytest.mark.parametrize("algorithm,ref_alg", [("hirschberg_myers", 0), ("myers", 1)])
+@pytest.mark.parametrize("algorithm,ref_alg", [("hirschberg_myers", 0), ("myers", 1), ("ukkonen", 2)])
 def test_vs_unmodified_reference_classes(algorithm, ref_alg):
     if not ref_lib.have_gwref():
         pytest.skip("oracle/_ref/libgwref.so not built")
     rng = random.Random(5)
     sizes = [10, 40, 62, 63, 64, 200, 333, 1000, 2000, 4000] if algorithm == "hirschberg_myers" else [10, 40, 63, 64, 200, 333, 1000, 1500]
-    pairs = random_pairs(rng, sizes) + [("", "ACGT"), ("ACGT", ""), ("A", "CCCCCA"), ("G", "CCCC")]
+    pairs = random_pairs(rng, sizes)
+    if algorithm != "ukkonen":
+        pairs += [("", "ACGT"), ("ACGT", ""), ("A", "CCCCCA"), ("G", "CCCC")]
+    else:
+        pairs += [(t, q) for q, t in random_pairs(rng, [50, 700])]  # query longer than target: swapped orientation
     max_q = max(len(q) for q, _ in pairs)
     max_t = max(len(t) for _, t in pairs)
     res = run_ours(pairs, algorithm, max_q=max_q, max_t=max_t)
@@ -133,3 +139,19 @@ def test_long_pair_hirschberg_vs_reference_and_banded_distance():
     ref = ref_lib.ref_global_aligner_run(q_len, q_data, t_len, t_data, 0, max_q, max_t)
     for i, a in enumerate(res):
         assert a.convert_to_cigar(extended=True) == ref["cigar_extended"][i]
+
+
+def test_ukkonen_vs_oracle_and_length_difference_status():
+    rng = random.Random(21)
+    pairs = random_pairs(rng, [3, 30, 64, 100, 257, 900, 2000])
+    pairs += [(t, q) for q, t in pairs[:4]]
+    res = run_ours(pairs, "ukkonen", max_q=2200, max_t=2200)
+    for a, (q, t) in zip(res, pairs):
+        st = ol.ukkonen_align(q, t)
+        assert a.status == cudaaligner.success and a.is_optimal
+        assert a.convert_to_cigar(extended=True) == ol.states_to_cigar(st, extended=True), (len(q), len(t))
+    al = cudaaligner.GlobalAligner(100, 100, 2, "ukkonen")
+    # more than 10 % of max_target_length apart (aligner_global_ukkonen.cpp:52-60)
+    assert al.add_alignment("A" * 50, "A" * 61) == cudaaligner.exceeded_max_alignment_difference
+    assert al.add_alignment("A" * 50, "A" * 60) == cudaaligner.success
+    al.close()

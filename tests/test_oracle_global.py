@@ -60,3 +60,22 @@ def test_random_pairs_are_optimal_alignments():
             assert not failed and consumes(st, q, t) and edit_distance(st) == d, (n, mq)
         st2 = ol.myers_full_align(q, t)
         assert consumes(st2, q, t) and edit_distance(st2) == d
+
+
+@pytest.mark.parametrize("q,t,cigar,dist", [k for k in KAT if k[0] and k[1]])
+def test_reference_table_ukkonen(q, t, cigar, dist):
+    # Test_AlignerGlobal.cpp:138: the Ukkonen rows share the Default table (empty sequences excluded, :151-152)
+    st = ol.ukkonen_align(q, t)
+    assert ol.states_to_cigar(st) == cigar and edit_distance(st) == dist
+
+
+def test_ukkonen_random_pairs_are_optimal_within_the_band():
+    rng = random.Random(4)
+    for n in (5, 40, 100, 300, 900):
+        ref = "".join(rng.choice("ACGT") for _ in range(n))
+        q = "".join(c for c in ref if rng.random() > 0.03)
+        t = "".join(c if rng.random() > 0.05 else rng.choice("ACGT") for c in ref)
+        st = ol.ukkonen_align(q, t)
+        assert consumes(st, q, t) and edit_distance(st) == plain_edit_distance(q, t)
+        st = ol.ukkonen_align(t, q)  # query longer than target: the swapped orientation
+        assert consumes(st, t, q) and edit_distance(st) == plain_edit_distance(q, t)

@@ -43,3 +43,17 @@ def test_reference_benchmark_helpers_compile(workdir):
     tu = workdir / "tu.cpp"
     tu.write_text('#include <file_location.hpp>\n#include "multi_batch.hpp"\n#include "single_batch.hpp"\nint main() { return 0; }\n')
     _gxx(["-fsyntax-only", "-I", str(workdir), "-I", os.path.join(REF, "cudapoa", "benchmarks"), str(tu)])
+
+
+def test_nvtx_range_is_real_under_gw_profiling(workdir):
+    """GW_NVTX_RANGE (reference cudautils.hpp:155-184): a scoped range object when GW_PROFILING is defined, nothing otherwise."""
+    src = workdir / "nvtx_probe.cpp"
+    src.write_text('#include <claraparabricks/genomeworks/utils/cudautils.hpp>\n'
+                   'int main() { GW_NVTX_RANGE(r, "probe"); return 0; }\n')
+    out = str(workdir / "nvtx_probe")
+    for flags in ([], ["-DGW_PROFILING"]):
+        _gxx(flags + [str(src), "-o", out, "-L", "/usr/local/cuda/lib64", "-lcudart", "-ldl"])
+        assert subprocess.run([out]).returncode == 0
+    pre = subprocess.run(["g++", "-std=c++14", "-E", "-DGW_PROFILING", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", str(src)],
+                         capture_output=True, text=True).stdout
+    assert "nvtx_range r(" in pre.replace("::claraparabricks::genomeworks::cudautils::", "")
