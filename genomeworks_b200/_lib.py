@@ -76,6 +76,9 @@ def lib():
         L.gwb200_aligner_last_cells.restype = C.c_int64
         L.gwb200_aligner_last_kernel_ms.argtypes = [C.c_void_p]
         L.gwb200_aligner_last_kernel_ms.restype = C.c_float
+    if hasattr(L, "gwb200_aligner_add_alignments"):
+        L.gwb200_aligner_add_alignments.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.gwb200_aligner_results_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     if hasattr(L, "gwb200_global_aligner_create"):
         L.gwb200_global_aligner_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                                    C.c_void_p, C.c_void_p, C.c_void_p]

@@ -494,6 +494,59 @@ int gwb200_aligner_result_runs(const gwb200_aligner* a, int32_t i, int8_t* actio
     return 0;
 }
 
+// The loop a C++ caller writes around add_alignment(), for FFI callers that pay per call: stops at the first pair that is not
+// admitted; *n_added pairs went in, the return value is the status of the last call.
+int gwb200_aligner_add_alignments(gwb200_aligner* a, int32_t n, const char* const* queries, const int32_t* query_lengths,
+                                  const char* const* targets, const int32_t* target_lengths, int32_t* n_added)
+{
+    int rc = GWB200_ALN_SUCCESS;
+    int32_t i = 0;
+    for (; i < n; ++i)
+    {
+        rc = gwb200_aligner_add_alignment(a, 0, queries[i], query_lengths[i], targets[i], target_lengths[i], 0, 0);
+        if (rc != GWB200_ALN_SUCCESS)
+            break;
+    }
+    if (n_added)
+        *n_added = i;
+    return rc;
+}
+
+// All results of the last sync in one call: status / is_optimal / run_offsets[n + 1] per alignment, the RLE entries of
+// alignment i at [run_offsets[i], run_offsets[i + 1]) of actions / runlengths (capacity entries; GWB200_E_INVALID_ARGUMENT if too small).
+int gwb200_aligner_results_flat(const gwb200_aligner* a, int32_t* status, int32_t* is_optimal, int64_t* run_offsets, int8_t* actions,
+                                int32_t* runlengths, int64_t capacity)
+{
+    if (!a)
+        return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
+    int64_t off = 0;
+    for (size_t i = 0; i < a->results.size(); ++i)
+    {
+        const AlnResult& r = a->results[i];
+        if (status)
+            status[i] = r.status;
+        if (is_optimal)
+            is_optimal[i] = r.is_optimal;
+        if (run_offsets)
+            run_offsets[i] = off;
+        const int64_t k = static_cast<int64_t>(r.actions.size());
+        if (actions && runlengths)
+        {
+            if (off + k > capacity)
+                return set_error(GWB200_E_INVALID_ARGUMENT, "results_flat: capacity too small");
+            if (k)
+            {
+                std::memcpy(actions + off, r.actions.data(), k);
+                std::memcpy(runlengths + off, r.runs.data(), k * 4);
+            }
+        }
+        off += k;
+    }
+    if (run_offsets)
+        run_offsets[a->results.size()] = off;
+    return 0;
+}
+
 int gwb200_aligner_reset(gwb200_aligner* a)
 {
     if (!a)

@@ -216,6 +216,7 @@ __device__ __forceinline__ void horizontal_fast(uint32_t mask, int32_t lane, Ban
     const WordType hb = WordType(1) << (lane == (n_words - 1) ? width - (n_words - 1) * kWord - 1 : kWord - 1);
     // the pattern of column t + 1 is fetched while column t is computed (neither load depends on the recurrence)
     WordType eq_next  = Q.get(lane, pattern_idx_offset, __ldg(target + t_begin - 1));
+    char tc_next      = t_begin + 1 < t_end ? __ldg(target + t_begin) : 'A'; // the character of column t + 1, loaded one column earlier still
     WordType* pvp     = &pvm(lane, t_begin);
     WordType* mvp     = &mvm(lane, t_begin);
     int32_t* scp      = &scm(lane, t_begin);
@@ -224,7 +225,9 @@ __device__ __forceinline__ void horizontal_fast(uint32_t mask, int32_t lane, Ban
     {
         const WordType eq = eq_next;
         if (t + 1 < t_end)
-            eq_next = Q.get(lane, pattern_idx_offset, __ldg(target + t));
+            eq_next = Q.get(lane, pattern_idx_offset, tc_next);
+        if (t + 2 < t_end)
+            tc_next = __ldg(target + t + 1);
         const int2 c = advance_block(mask, lane, hb, eq, R.pv, R.mv, lane == 0 ? 1 : 0);
         R.sc += c.x;
         *pvp = R.pv;
@@ -247,6 +250,7 @@ __device__ __forceinline__ void diagonal_fast(uint32_t mask, int32_t lane, BandR
     const WordType ddb   = drb << 1;
     const bool has_above = (mask >> lane) > 1u;
     WordType eq_next     = Q.get(lane, 1, __ldg(target + t_begin - 1));
+    char tc_next         = t_begin + 1 < t_end ? __ldg(target + t_begin) : 'A';
     WordType* pvp        = &pvm(lane, t_begin);
     WordType* mvp        = &mvm(lane, t_begin);
     int32_t* scp         = &scm(lane, t_begin);
@@ -255,7 +259,9 @@ __device__ __forceinline__ void diagonal_fast(uint32_t mask, int32_t lane, BandR
     {
         const WordType eq = eq_next;
         if (t + 1 < t_end)
-            eq_next = Q.get(lane, t - t_begin + 2, __ldg(target + t));
+            eq_next = Q.get(lane, t - t_begin + 2, tc_next);
+        if (t + 2 < t_end)
+            tc_next = __ldg(target + t + 1);
         // previous column shifted down by one row: warp_rightshift_sync on pv and mv (myers_gpu.cu:91-102, 705-706)
         const uint32_t lows = (R.pv & 1u) | ((R.mv & 1u) << 1);
         const uint32_t in   = __shfl_down_sync(mask, lows, 1);
@@ -456,6 +462,7 @@ struct Stage
     int32_t n_words_band;
     int32_t jlo, jhi; // staged columns [jlo, jhi]; jhi < jlo => nothing staged
     int32_t sstride;  // words per staged column
+    int32_t sbase;    // index of the first staged word (bulk copies start at a 16-byte boundary)
     unsigned long long* bar; // mbarrier of the bulk copies and its next wait parity (kept across alignments: the barrier lives with the CTA)
     uint32_t phase;
     bool use_smem;
@@ -471,17 +478,22 @@ struct Stage
         jlo = max(0, j - kStageCols + 1);
         const int32_t n_el = (jhi - jlo + 1) * n_words_band;
         const int64_t off  = static_cast<int64_t>(jlo) * n_words_band;
-        if ((n_words_band & 3) == 0 && ((reinterpret_cast<uintptr_t>(pvm.data) | reinterpret_cast<uintptr_t>(mvm.data) | reinterpret_cast<uintptr_t>(scm.data)) & 15) == 0)
+        if (((reinterpret_cast<uintptr_t>(pvm.data) | reinterpret_cast<uintptr_t>(mvm.data) | reinterpret_cast<uintptr_t>(scm.data)) & 15) == 0)
         {
-            sstride = n_words_band;
+            // any number of words per column: the copy starts at the 16-byte boundary below the block and ends at the one above it
+            // (the workspaces carry 64 elements of slack), the stage remembers the shift
+            sstride             = n_words_band;
+            sbase               = static_cast<int32_t>(off & 3);
+            const int64_t off_a = off - sbase;
+            const int32_t n_a   = (n_el + sbase + 3) & ~3;
             if (lane == 0)
             {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of the stage vs. the async writes
-                const uint32_t bytes = static_cast<uint32_t>(n_el) * 4u;
+                const uint32_t bytes = static_cast<uint32_t>(n_a) * 4u;
                 mbar_arrive_expect_tx(bar, 3u * bytes);
-                bulk_load_g2s(s_pv, pvm.data + off, bytes, bar);
-                bulk_load_g2s(s_mv, mvm.data + off, bytes, bar);
-                bulk_load_g2s(s_sc, scm.data + off, bytes, bar);
+                bulk_load_g2s(s_pv, pvm.data + off_a, bytes, bar);
+                bulk_load_g2s(s_mv, mvm.data + off_a, bytes, bar);
+                bulk_load_g2s(s_sc, scm.data + off_a, bytes, bar);
             }
             __syncwarp();
             mbar_wait(bar, phase);
@@ -490,6 +502,7 @@ struct Stage
         else
         {
             sstride = kStageStride;
+            sbase   = 0;
             for (int32_t e = lane; e < n_el; e += 32)
             {
                 const int32_t c = e / n_words_band;
@@ -513,7 +526,7 @@ struct Stage
         WordType p, m;
         if (use_smem)
         {
-            const int32_t o = (j - jlo) * sstride + word_idx;
+            const int32_t o = sbase + (j - jlo) * sstride + word_idx;
             s = s_sc[o];
             p = s_pv[o];
             m = s_mv[o];
@@ -773,9 +786,9 @@ __device__ __forceinline__ int32_t fetch_task(const DeviceParams& P, int32_t lan
 // myers_banded_kernel, myers_gpu.cu:862-1032
 __global__ void __launch_bounds__(32, 12) myers_banded_kernel(const DeviceParams P)
 {
-    __shared__ __align__(16) WordType s_pv[kStageCols * kStageStride];
-    __shared__ __align__(16) WordType s_mv[kStageCols * kStageStride];
-    __shared__ __align__(16) int32_t s_sc[kStageCols * kStageStride];
+    __shared__ __align__(16) WordType s_pv[kStageCols * kStageStride + 8];
+    __shared__ __align__(16) WordType s_mv[kStageCols * kStageStride + 8];
+    __shared__ __align__(16) int32_t s_sc[kStageCols * kStageStride + 8];
     __shared__ __align__(16) WordType s_qpat[4 * (kQpatSmemWords + 1)];
     __shared__ unsigned long long s_bar;
     uint32_t bar_phase = 0;
@@ -928,6 +941,7 @@ __global__ void __launch_bounds__(32, 12) myers_banded_kernel(const DeviceParams
             S.jhi          = -1;
             S.use_smem     = n_words_band <= 32;
             S.sstride      = kStageStride;
+            S.sbase        = 0;
             S.bar          = &s_bar;
             S.phase        = bar_phase;
             path_length    = backtrace_banded(lane, S, out_actions, out_runs, diagonal_begin, diagonal_end, abs(band_width), target_size);

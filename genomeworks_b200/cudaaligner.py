@@ -155,8 +155,38 @@ class FixedBandAligner:
             self._pairs.append((_revcomp(q) if reverse_complement_query else q, _revcomp(t) if reverse_complement_target else t))
         return rc
 
+    def add_alignments(self, pairs):
+        """add_alignment() for a list of (query, target) byte strings in one call into the engine (the loop a C++ caller writes).
+        Returns (status of the last call, number of pairs added)."""
+        n = len(pairs)
+        qs = (C.c_char_p * n)(*[p[0] for p in pairs])
+        ts = (C.c_char_p * n)(*[p[1] for p in pairs])
+        ql = (C.c_int32 * n)(*[len(p[0]) for p in pairs])
+        tl = (C.c_int32 * n)(*[len(p[1]) for p in pairs])
+        added = C.c_int32(0)
+        rc = check(lib().gwb200_aligner_add_alignments(self._h, C.c_int32(n), qs, ql, ts, tl, C.byref(added)))
+        self._pairs.extend(pairs[:added.value])
+        return rc, added.value
+
     def align_all(self):
         return check(lib().gwb200_aligner_align_all(self._h))
+
+    def sync_alignments_flat(self):
+        """sync_alignments() with all results fetched in one call: returns (status, is_optimal, run_offsets, actions, runlengths)
+        numpy arrays; get_alignments() stays empty."""
+        rc = check(lib().gwb200_aligner_sync_alignments(self._h))
+        n = len(self._pairs)
+        cap = sum(len(q) + len(t) for q, t in self._pairs) + 16
+        st = np.zeros(n, dtype=np.int32)
+        opt = np.zeros(n, dtype=np.int32)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        act = np.zeros(cap, dtype=np.int8)
+        runs = np.zeros(cap, dtype=np.int32)
+        check(lib().gwb200_aligner_results_flat(self._h, st.ctypes.data, opt.ctypes.data, offs.ctypes.data, act.ctypes.data, runs.ctypes.data,
+                                                C.c_int64(cap)))
+        self._pairs = []
+        self._results = []
+        return st, opt, offs, act[:offs[n]], runs[:offs[n]]
 
     def sync_alignments(self, want_strings=True):
         rc = check(lib().gwb200_aligner_sync_alignments(self._h))

@@ -149,9 +149,10 @@ def sharded_consensus(win_nseq, seq_len, seq_data, make_batch, dist, device=None
     batch.close()
     to = (lambda a: torch.from_numpy(a).to(device)) if device is not None else torch.from_numpy
     g_cons = gather_fixed_stride(to(cons), idx, n_total, dist, device=device, dst=src)
-    g_cov = gather_fixed_stride(to(cov.view(np.int16)), idx, n_total, dist, device=device, dst=src)
+    # coverage travels as bytes: 16-bit integers are not a collective dtype of every backend (gloo rejects them)
+    g_cov = gather_fixed_stride(to(cov.view(np.uint8)), idx, n_total, dist, device=device, dst=src)
     g_meta = gather_fixed_stride(to(meta), idx, n_total, dist, device=device, dst=src)
     if dist.get_rank() != src:
         return None
     g_meta = g_meta.cpu().numpy()
-    return dict(consensus=g_cons.cpu().numpy(), coverage=g_cov.cpu().numpy().view(np.uint16), lengths=g_meta[:, 0], status=g_meta[:, 1])
+    return dict(consensus=g_cons.cpu().numpy(), coverage=np.ascontiguousarray(g_cov.cpu().numpy()).view(np.uint16), lengths=g_meta[:, 0], status=g_meta[:, 1])

@@ -254,6 +254,12 @@ int gwb200_aligner_result_info(const gwb200_aligner* aligner, int32_t i, int32_t
 int gwb200_aligner_result_runs(const gwb200_aligner* aligner, int32_t i, int8_t* actions, int32_t* runlengths);
 /* Aligner::reset(), aligner.hpp:112 ; FixedBandAligner::reset_max_bandwidth(), aligner.hpp:153 ;
  * Aligner::free_temporary_device_buffers(), aligner.hpp:124 */
+/* Convenience for FFI callers (not part of the reference surface): the loop a C++ caller writes around add_alignment(), and all
+ * results of the last sync_alignments() in one call (run_offsets[n + 1]; entries of alignment i at [run_offsets[i], run_offsets[i + 1])). */
+int gwb200_aligner_add_alignments(gwb200_aligner* aligner, int32_t n, const char* const* queries, const int32_t* query_lengths,
+                                  const char* const* targets, const int32_t* target_lengths, int32_t* n_added);
+int gwb200_aligner_results_flat(const gwb200_aligner* aligner, int32_t* status, int32_t* is_optimal, int64_t* run_offsets, int8_t* actions,
+                                int32_t* runlengths, int64_t capacity);
 int gwb200_aligner_reset(gwb200_aligner* aligner);
 int gwb200_aligner_reset_max_bandwidth(gwb200_aligner* aligner, int32_t max_bandwidth);
 int gwb200_aligner_free_temporary_device_buffers(gwb200_aligner* aligner);

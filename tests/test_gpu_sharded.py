@@ -66,7 +66,18 @@ def test_two_rank_sharded_consensus_equals_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, backend, q)) for r in range(2)]
     for p in procs:
         p.start()
-    ok = q.get(timeout=600)
+    import queue as _queue
+    ok = None
+    for _ in range(300):
+        try:
+            ok = q.get(timeout=1)
+            break
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break  # a rank died: fail now instead of waiting for the timeout
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
+        if p.is_alive():
+            p.terminate()
+    assert ok is not None, "a rank failed before producing a result (backend %s)" % backend
     assert ok, "sharded consensus differs from the single-GPU result (backend %s)" % backend

@@ -49,7 +49,7 @@ def test_reference_msa_case_equals_spoa(accurate):
     msa, status = b.get_msa()
     b.close()
     assert status[0] == 0 and len(msa[0]) == 500
-    assert msa[0] == spoa_rows
+    assert [r.decode() if isinstance(r, bytes) else r for r in msa[0]] == spoa_rows
 
 
 def test_default_mode_is_unchanged():
