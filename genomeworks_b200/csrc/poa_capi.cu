@@ -275,6 +275,8 @@ int32_t v3_action(gwb200_poa_batch* b, int action)
     // the wavefront rows (poa_kernels_v4.cuh, 32-bit scores) live in their own instantiation: its code and register budget
     // do not weigh on the default kernel
     auto kfn = poa_window_kernel_v3<ScoreT, SizeT, true, false>;
+    if (b->Y.use_bulk == 0)
+        kfn = poa_window_kernel_v3<ScoreT, SizeT, false, false>; // rows leave by per-lane vector stores (A/B switch GWB200_POA_BULK=0)
     if constexpr (sizeof(ScoreT) == 4)
     {
         if (b->Y.wavefront != 0)
