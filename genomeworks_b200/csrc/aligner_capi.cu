@@ -8,6 +8,7 @@
 #include "myers_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -291,8 +292,8 @@ int gwb200_aligner_add_alignment(gwb200_aligner* a, int32_t max_bandwidth, const
 {
     if (!a)
         return set_error(GWB200_E_INVALID_ARGUMENT, "null aligner");
-    if (max_bandwidth <= 0)
-        max_bandwidth = a->max_bandwidth;
+    if (max_bandwidth == GWB200_ALN_DEFAULT_BANDWIDTH)
+        max_bandwidth = a->max_bandwidth; // Aligner::add_alignment without a bandwidth (aligner_global_myers_banded.cpp:155-158)
     if (max_bandwidth < 0 || query_length < 0 || target_length < 0 || query == nullptr || target == nullptr)
         return GWB200_ALN_GENERIC_ERROR;
     const int32_t n = a->num_alignments();
@@ -351,11 +352,19 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     const int32_t qpat_el  = 4 * ((a->max_query + 31) / 32) + 4;
     const int64_t ws       = std::max<int64_t>(a->max_matrix, 1);
     const int64_t ws_pitch = (ws + 3) & ~3ll; // 16-byte aligned workspaces: the backtrace stages them by bulk copies
+    // a second workspace per CTA lets the pass of the doubled Ukkonen estimate run alongside the current one; only when the
+    // budget the caller gave covers it (admission keeps counting one workspace per CTA, like the reference)
+    bool speculate = true;
+    if (const char* e = std::getenv("GWB200_MYERS_SPECULATE"))
+        speculate = std::atoi(e) != 0;
+    if (speculate && memory_requirement(a, 2 * a->max_matrix, a->max_query, seq_sum, n) >= a->max_device_memory)
+        speculate = false;
+    const int64_t ws_count = static_cast<int64_t>(n_blocks) * (speculate ? 2 : 1);
     bool ok = a->seq_d.ensure(seq_sum + 16) && a->seq_starts_d.ensure(2ll * n + 1) && a->max_bw_d.ensure(n) && a->sched_d.ensure(n) &&
               a->counter_d.ensure(1) && a->path_len_d.ensure(n) && a->offsets_d.ensure(n + 1) && a->metadata_d.ensure(n) &&
               a->slot_actions_d.ensure(seq_sum + 16) && a->slot_runs_d.ensure(seq_sum + 16) && a->actions_d.ensure(seq_sum + 16) &&
-              a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(ws_pitch * n_blocks) && a->mv_d.ensure(ws_pitch * n_blocks) &&
-              a->score_d.ensure(ws_pitch * n_blocks) && a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
+              a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(ws_pitch * ws_count) && a->mv_d.ensure(ws_pitch * ws_count) &&
+              a->score_d.ensure(ws_pitch * ws_count) && a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
               a->offsets_h.ensure(n + 1, false) && a->metadata_h.ensure(n, false) && a->cells_h.ensure(1, false);
     if (!ok)
         return set_error(GWB200_E_RUNTIME, "Out of memory.");
@@ -387,6 +396,7 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     P.score         = a->score_d.p;
     P.ws_elems      = ws;
     P.ws_stride     = ws_pitch;
+    P.speculate     = speculate ? 1 : 0;
     P.qpat          = a->qpat_d.p;
     P.qpat_elems    = qpat_el;
     P.slot_actions  = a->slot_actions_d.p;
@@ -398,7 +408,7 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     // residency (kBlocksPerSM) assumes the full shared-memory carve-out regardless of any device-wide cache preference
     cudaFuncSetAttribute(myers_banded_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     GWB200_CUDA_TRY(cudaEventRecord(a->ev0, a->stream));
-    myers_banded_kernel<<<n_blocks, 32, 0, a->stream>>>(P);
+    myers_banded_kernel<<<n_blocks, 64, 0, a->stream>>>(P);
     offsets_kernel<<<1, 1024, 0, a->stream>>>(a->path_len_d.p, n, a->offsets_d.p);
     compact_kernel<<<(n * 32 + 255) / 256, 256, 0, a->stream>>>(P, a->offsets_d.p, a->actions_d.p, a->runs_d.p);
     count_launch(3);
@@ -503,7 +513,7 @@ int gwb200_aligner_add_alignments(gwb200_aligner* a, int32_t n, const char* cons
     int32_t i = 0;
     for (; i < n; ++i)
     {
-        rc = gwb200_aligner_add_alignment(a, 0, queries[i], query_lengths[i], targets[i], target_lengths[i], 0, 0);
+        rc = gwb200_aligner_add_alignment(a, GWB200_ALN_DEFAULT_BANDWIDTH, queries[i], query_lengths[i], targets[i], target_lengths[i], 0, 0);
         if (rc != GWB200_ALN_SUCCESS)
             break;
     }

@@ -49,7 +49,8 @@ struct DeviceParams
     WordType* mv;
     int32_t* score;
     int64_t ws_elems;            // elements per CTA in pv / mv / score
-    int64_t ws_stride;           // distance between the CTAs' workspaces (ws_elems rounded up to 4 elements: 16-byte aligned)
+    int64_t ws_stride;           // distance between workspaces (ws_elems rounded up to 4 elements: 16-byte aligned)
+    int32_t speculate;           // 1: two workspaces per CTA, the pass of the doubled estimate runs alongside (see the kernel)
     WordType* qpat;
     int32_t qpat_elems;          // elements per CTA (>= 4 * ceil(max_query/32))
     // per-alignment result slots: alignment i owns [seq_starts[2i], seq_starts[2i+2])
@@ -783,32 +784,83 @@ __device__ __forceinline__ int32_t fetch_task(const DeviceParams& P, int32_t lan
     return k < P.n_alignments ? P.sched_index[k] : P.n_alignments;
 }
 
-// myers_banded_kernel, myers_gpu.cu:862-1032
-__global__ void __launch_bounds__(32, 12) myers_banded_kernel(const DeviceParams P)
+// One pass of the Ukkonen loop (myers_gpu.cu:955-1002): its band for the estimate of pass k, whether it fits the workspace
+struct PassPlan
+{
+    int32_t estimate, p, band_width, n_words_band;
+    bool fits;
+};
+__device__ __forceinline__ PassPlan plan_pass(int32_t k, int32_t query_size, int32_t target_size, int32_t max_bandwidth, int64_t ws_elems)
+{
+    PassPlan r;
+    const int32_t diff = abs(target_size - query_size);
+    const int64_t e0   = max(1, diff + min(target_size, query_size) / 20);
+    const int64_t ek   = e0 << min(k, 30);
+    r.estimate         = static_cast<int32_t>(ek < static_cast<int64_t>(INT32_MAX) ? ek : static_cast<int64_t>(INT32_MAX)); // bands stop growing long before this saturates
+    int32_t p          = min(min(target_size, query_size), (r.estimate - diff) / 2);
+    int32_t bw         = min(1 + 2 * p + diff, query_size);
+    if (bw % kWord == 1 && bw != query_size)
+    {
+        p += 1;
+        bw = min(1 + 2 * p + diff, query_size);
+    }
+    if (bw > max_bandwidth)
+    {
+        bw = max_bandwidth;
+        p  = (bw - 1 - diff) / 2;
+    }
+    r.p            = p;
+    r.band_width   = bw;
+    r.n_words_band = ceil_div(bw, kWord);
+    r.fits         = static_cast<int64_t>(r.n_words_band) * static_cast<int64_t>(target_size + 1) <= ws_elems;
+    return r;
+}
+
+// myers_banded_kernel, myers_gpu.cu:862-1032. One alignment per CTA of two warps: the Ukkonen loop runs two passes at a time,
+// warp 0 the pass of the current estimate and warp 1 -- speculatively, in a workspace of its own -- the pass of the doubled
+// estimate, so that an alignment whose first band is too narrow does not pay the passes one after the other (C4: about half the
+// pairs need the second band). The decisions are then taken in the reference's order, a speculative pass the sequential loop would
+// not have reached is dropped and not counted in the executed cells. The warp that owns the final pass does the backtrace.
+__global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams P)
 {
     __shared__ __align__(16) WordType s_pv[kStageCols * kStageStride + 8];
     __shared__ __align__(16) WordType s_mv[kStageCols * kStageStride + 8];
     __shared__ __align__(16) int32_t s_sc[kStageCols * kStageStride + 8];
     __shared__ __align__(16) WordType s_qpat[4 * (kQpatSmemWords + 1)];
     __shared__ unsigned long long s_bar;
-    uint32_t bar_phase = 0;
+    __shared__ uint32_t s_phase;
+    __shared__ int32_t s_task;
+    __shared__ int32_t s_dist[2], s_dbeg[2], s_dend[2];
+    const int32_t lane = threadIdx.x & 31;
+    const int32_t warp = threadIdx.x >> 5;
     if (threadIdx.x == 0)
     {
         mbar_init(&s_bar, 1);
+        s_phase = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    __syncthreads();
 
-    const int32_t lane = threadIdx.x;
-    WordType* qpat     = P.qpat + static_cast<int64_t>(blockIdx.x) * P.qpat_elems;
-    WordType* pv_ws    = P.pv + static_cast<int64_t>(blockIdx.x) * P.ws_stride;
-    WordType* mv_ws    = P.mv + static_cast<int64_t>(blockIdx.x) * P.ws_stride;
-    int32_t* sc_ws     = P.score + static_cast<int64_t>(blockIdx.x) * P.ws_stride;
+    WordType* qpat  = P.qpat + static_cast<int64_t>(blockIdx.x) * P.qpat_elems;
+    // workspace of this warp's passes (P.speculate == 0: one workspace per CTA, warp 1 only helps with the patterns)
+    const int64_t ws_index = static_cast<int64_t>(blockIdx.x) * (P.speculate ? 2 : 1) + (P.speculate ? warp : 0);
+    WordType* pv_ws = P.pv + ws_index * P.ws_stride;
+    WordType* mv_ws = P.mv + ws_index * P.ws_stride;
+    int32_t* sc_ws  = P.score + ws_index * P.ws_stride;
     unsigned long long my_cells = 0;
 
-    int32_t a = fetch_task(P, lane);
-    while (a < P.n_alignments)
+    for (;;)
     {
+        if (threadIdx.x == 0)
+        {
+            const int32_t k = atomicAdd(P.sched_counter, 1);
+            s_task          = k < P.n_alignments ? P.sched_index[k] : P.n_alignments;
+        }
+        __syncthreads();
+        const int32_t a = s_task;
+        __syncthreads();
+        if (a >= P.n_alignments)
+            break;
         const char* const query   = P.seqs + P.seq_starts[2 * a];
         const char* const target  = P.seqs + P.seq_starts[2 * a + 1];
         const int32_t query_size  = static_cast<int32_t>(P.seq_starts[2 * a + 1] - P.seq_starts[2 * a]);
@@ -820,17 +872,16 @@ __global__ void __launch_bounds__(32, 12) myers_banded_kernel(const DeviceParams
 
         if (max_bandwidth - 1 < abs(target_size - query_size) && query_size != 0 && target_size != 0)
         {
-            if (lane == 0)
+            if (threadIdx.x == 0)
             {
                 P.path_len[a] = 0;
                 P.metadata[a] = static_cast<uint32_t>(a);
             }
-            a = fetch_task(P, lane);
             continue;
         }
         if (target_size == 0 || query_size == 0)
         {
-            if (lane == 0)
+            if (threadIdx.x == 0)
             {
                 if (query_size == 0 && target_size == 0)
                 {
@@ -844,12 +895,10 @@ __global__ void __launch_bounds__(32, 12) myers_banded_kernel(const DeviceParams
                 }
                 P.metadata[a] = static_cast<uint32_t>(a) | (1u << 31);
             }
-            a = fetch_task(P, lane);
             continue;
         }
-        __syncwarp();
-        // query bit patterns, [n_words x 4] with character order A,C,T,G (:938-947)
-        for (int32_t idx = lane; idx < n_words; idx += 32)
+        // query bit patterns, [n_words x 4] with character order A,C,T,G (:938-947), built by both warps
+        for (int32_t idx = threadIdx.x; idx < n_words; idx += 64)
         {
             const int32_t off   = idx * kWord;
             const int32_t max_i = min(query_size - off, kWord);
@@ -874,88 +923,142 @@ __global__ void __launch_bounds__(32, 12) myers_banded_kernel(const DeviceParams
                 s_qpat[3 * (n_words + 1) + idx] = rG;
             }
         }
-        if (n_words <= kQpatSmemWords && lane < 4)
-            s_qpat[lane * (n_words + 1) + n_words] = 0;
-        __syncwarp();
+        if (n_words <= kQpatSmemWords && threadIdx.x < 4)
+            s_qpat[threadIdx.x * (n_words + 1) + n_words] = 0;
+        __threadfence_block();
+        __syncthreads();
         QPat Q;
         Q.sbase   = n_words <= kQpatSmemWords ? smem_addr(s_qpat) : 0u;
         Q.gbase   = qpat;
         Q.n_words = n_words;
 
-        // Ukkonen band doubling (:955-1002)
-        int32_t max_distance_estimate = max(1, abs(target_size - query_size) + min(target_size, query_size) / 20);
+        // ---- Ukkonen band doubling (:955-1002), two passes per round
         View<WordType> pvm{pv_ws, 0}, mvm{mv_ws, 0};
         View<int32_t> scm{sc_ws, 0};
-        int32_t diagonal_begin = -1, diagonal_end = -1, band_width = 0, n_words_band = 0;
-        while (1)
+        int32_t band_width = 0;   // of the pass the walk runs on; negative = not optimal; 0 = nothing fits
+        int32_t winner     = 0;   // the warp that owns that pass
+        int32_t prev_band = 0, prev_owner = 0; // the last pass that ran, for "the next one does not fit"
+        const int32_t step = P.speculate ? 2 : 1;
+        for (int32_t k0 = 0;; k0 += step)
         {
-            int32_t p              = min(min(target_size, query_size), (max_distance_estimate - abs(target_size - query_size)) / 2);
-            int32_t band_width_new = min(1 + 2 * p + abs(target_size - query_size), query_size);
-            if (band_width_new % kWord == 1 && band_width_new != query_size)
+            const PassPlan A = plan_pass(k0, query_size, target_size, max_bandwidth, P.ws_elems);
+            const PassPlan B = plan_pass(k0 + 1, query_size, target_size, max_bandwidth, P.ws_elems);
+            // pass A ends the loop by itself (whatever its distance) when its band is the whole query or the largest allowed
+            const bool a_final = A.band_width == query_size || A.band_width == max_bandwidth;
+            const bool run_b   = P.speculate && A.fits && !a_final && B.fits;
+            const PassPlan& M  = (warp == 0) ? A : B;
+            if ((warp == 0 && A.fits) || (warp == 1 && run_b))
             {
-                p += 1;
-                band_width_new = min(1 + 2 * p + abs(target_size - query_size), query_size);
+                pvm.rows = M.n_words_band;
+                mvm.rows = M.n_words_band;
+                scm.rows = M.n_words_band;
+                int32_t db = -1, de = -1;
+                compute_scores_banded(lane, db, de, pvm, mvm, scm, Q, qpat, n_words, target, target_size, query_size, M.band_width, M.n_words_band, M.p);
+                __syncwarp();
+                if (lane == 0)
+                {
+                    s_dist[warp] = M.n_words_band > 0 ? scm(M.n_words_band - 1, target_size) : target_size;
+                    s_dbeg[warp] = db;
+                    s_dend[warp] = de;
+                }
             }
-            if (band_width_new > max_bandwidth)
+            __syncthreads();
+            bool done = false;
+            if (!A.fits)
             {
-                band_width_new = max_bandwidth;
-                p              = (band_width_new - 1 - abs(target_size - query_size)) / 2;
+                band_width = -prev_band;
+                winner     = prev_owner;
+                done       = true;
             }
-            const int32_t nwb = ceil_div(band_width_new, kWord);
-            if (static_cast<int64_t>(nwb) * static_cast<int64_t>(target_size + 1) > P.ws_elems)
+            else
             {
-                band_width = -band_width;
+                if (threadIdx.x == 0)
+                    my_cells += static_cast<unsigned long long>(A.band_width) * static_cast<unsigned long long>(target_size);
+                prev_band  = A.band_width;
+                prev_owner = 0;
+                if (s_dist[0] <= A.estimate || A.band_width == query_size)
+                {
+                    band_width = A.band_width;
+                    winner     = 0;
+                    done       = true;
+                }
+                else if (A.band_width == max_bandwidth)
+                {
+                    band_width = -A.band_width;
+                    winner     = 0;
+                    done       = true;
+                }
+                else if (P.speculate)
+                {
+                    if (!B.fits)
+                    {
+                        band_width = -A.band_width;
+                        winner     = 0;
+                        done       = true;
+                    }
+                    else
+                    {
+                        if (threadIdx.x == 0)
+                            my_cells += static_cast<unsigned long long>(B.band_width) * static_cast<unsigned long long>(target_size);
+                        prev_band  = B.band_width;
+                        prev_owner = 1;
+                        if (s_dist[1] <= B.estimate || B.band_width == query_size)
+                        {
+                            band_width = B.band_width;
+                            winner     = 1;
+                            done       = true;
+                        }
+                        else if (B.band_width == max_bandwidth)
+                        {
+                            band_width = -B.band_width;
+                            winner     = 1;
+                            done       = true;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (done)
                 break;
-            }
-            band_width   = band_width_new;
-            n_words_band = nwb;
-            pvm.rows     = nwb;
-            mvm.rows     = nwb;
-            scm.rows     = nwb;
-            my_cells += static_cast<unsigned long long>(band_width) * static_cast<unsigned long long>(target_size);
-            compute_scores_banded(lane, diagonal_begin, diagonal_end, pvm, mvm, scm, Q, qpat, n_words, target, target_size, query_size, band_width,
-                                  nwb, p);
-            __syncwarp();
-            const int32_t cur_edit_distance = nwb > 0 ? scm(nwb - 1, target_size) : target_size;
-            if (cur_edit_distance <= max_distance_estimate || band_width == query_size)
-                break;
-            if (band_width == max_bandwidth)
-            {
-                band_width = -band_width;
-                break;
-            }
-            max_distance_estimate *= 2;
         }
-        int32_t path_length = 0;
-        if (band_width != 0)
+        if (warp == winner)
         {
-            Stage S;
-            S.s_pv         = s_pv;
-            S.s_mv         = s_mv;
-            S.s_sc         = s_sc;
-            S.pvm          = pvm;
-            S.mvm          = mvm;
-            S.scm          = scm;
-            S.n_words_band = n_words_band;
-            S.jlo          = 0;
-            S.jhi          = -1;
-            S.use_smem     = n_words_band <= 32;
-            S.sstride      = kStageStride;
-            S.sbase        = 0;
-            S.bar          = &s_bar;
-            S.phase        = bar_phase;
-            path_length    = backtrace_banded(lane, S, out_actions, out_runs, diagonal_begin, diagonal_end, abs(band_width), target_size);
-            bar_phase      = S.phase;
+            int32_t path_length = 0;
+            if (band_width != 0)
+            {
+                const int32_t bw  = abs(band_width);
+                const int32_t nwb = ceil_div(bw, kWord);
+                pvm.rows          = nwb;
+                mvm.rows          = nwb;
+                scm.rows          = nwb;
+                Stage S;
+                S.s_pv         = s_pv;
+                S.s_mv         = s_mv;
+                S.s_sc         = s_sc;
+                S.pvm          = pvm;
+                S.mvm          = mvm;
+                S.scm          = scm;
+                S.n_words_band = nwb;
+                S.jlo          = 0;
+                S.jhi          = -1;
+                S.use_smem     = nwb <= 32;
+                S.sstride      = kStageStride;
+                S.sbase        = 0;
+                S.bar          = &s_bar;
+                S.phase        = s_phase;
+                path_length    = backtrace_banded(lane, S, out_actions, out_runs, s_dbeg[warp], s_dend[warp], bw, target_size);
+                if (lane == 0)
+                    s_phase = S.phase;
+            }
+            if (lane == 0)
+            {
+                P.path_len[a] = path_length;
+                P.metadata[a] = static_cast<uint32_t>(a) | ((band_width > 0) ? (1u << 31) : 0u);
+            }
         }
-        if (lane == 0)
-        {
-            P.path_len[a] = path_length;
-            P.metadata[a] = static_cast<uint32_t>(a) | ((band_width > 0) ? (1u << 31) : 0u);
-        }
-        a = fetch_task(P, lane);
-        __syncwarp();
+        __syncthreads();
     }
-    if (lane == 0 && my_cells)
+    if (threadIdx.x == 0 && my_cells)
         atomicAdd(P.cells, my_cells);
 }
 

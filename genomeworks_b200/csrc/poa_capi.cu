@@ -1051,6 +1051,7 @@ int gwb200_poa_batch_add_groups_flat(gwb200_poa_batch* b, int32_t n_windows, con
         }
     } flush{b, jobs};
     b->deferred = &jobs;
+    int last_soft = GWB200_POA_SUCCESS; // empty_poa_group of some window: reported, but the remaining windows are still added
     for (int32_t w = 0; w < n_windows; w++)
     {
         const int32_t ns = win_nseq[w];
@@ -1064,14 +1065,18 @@ int gwb200_poa_batch_add_groups_flat(gwb200_poa_batch* b, int32_t n_windows, con
             o += seq_len[si + s];
         }
         int rc = gwb200_poa_batch_add_group(b, ns, seqs.data(), weights ? wts.data() : nullptr, seq_len + si, nullptr, nullptr);
-        if (rc != GWB200_POA_SUCCESS)
+        // a group whose reads were all rejected was consumed all the same (it stays in the batch as an empty window,
+        // cudapoa_batch.cuh:139-148): the caller's window <-> result mapping must count it
+        if (rc != GWB200_POA_SUCCESS && rc != GWB200_POA_EMPTY_POA_GROUP)
             return rc;
+        if (rc == GWB200_POA_EMPTY_POA_GROUP)
+            last_soft = rc;
         off = o;
         si += ns;
         if (n_added)
             *n_added = w + 1;
     }
-    return GWB200_POA_SUCCESS;
+    return last_soft;
 }
 
 int32_t gwb200_poa_batch_total_poas(const gwb200_poa_batch* b) { return b ? b->poa_count : 0; }

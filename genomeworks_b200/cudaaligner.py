@@ -143,7 +143,9 @@ class FixedBandAligner:
         check(lib().gwb200_aligner_create(C.byref(self._h), C.c_int32(max_bandwidth), C.c_void_p(st), C.c_int32(device_id),
                                           C.c_int64(int(max_device_memory))))
 
-    def add_alignment(self, query, target, max_bandwidth=0, reverse_complement_query=False, reverse_complement_target=False):
+    def add_alignment(self, query, target, max_bandwidth=None, reverse_complement_query=False, reverse_complement_target=False):
+        if max_bandwidth is None:
+            max_bandwidth = -2147483648  # GWB200_ALN_DEFAULT_BANDWIDTH: the aligner's own
         q = query.encode("utf-8") if isinstance(query, str) else bytes(query)
         t = target.encode("utf-8") if isinstance(target, str) else bytes(target)
         rc = check(lib().gwb200_aligner_add_alignment(self._h, C.c_int32(max_bandwidth), q, C.c_int32(len(q)), t, C.c_int32(len(t)),

@@ -98,7 +98,7 @@ public:
     StatusType add_alignment(const char* query, int32_t query_length, const char* target, int32_t target_length, bool rc_q = false,
                              bool rc_t = false) override
     {
-        return add_alignment(0, query, query_length, target, target_length, rc_q, rc_t);
+        return add_alignment(GWB200_ALN_DEFAULT_BANDWIDTH, query, query_length, target, target_length, rc_q, rc_t);
     }
     StatusType add_alignment(int32_t max_bandwidth, const char* query, int32_t query_length, const char* target, int32_t target_length,
                              bool rc_q = false, bool rc_t = false) override

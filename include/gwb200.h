@@ -140,8 +140,10 @@ void gwb200_poa_batch_destroy(gwb200_poa_batch* batch);
 int gwb200_poa_batch_add_group(gwb200_poa_batch* batch, int32_t n, const char* const* seqs, const int8_t* const* weights,
                                const int32_t* lengths, int32_t* per_seq_status, int32_t* n_per_seq);
 /* Bulk form of the same call for flat callers (Python): windows [first, first+count) of a flat window list
- * (win_nseq[], seq_len[], concatenated seq_data, optional concatenated weights). Stops at the first window that does not
- * return success; *n_added = windows accepted; returns that window's StatusType (success if all were added). */
+ * (win_nseq[], seq_len[], concatenated seq_data, optional concatenated weights). Stops at the first window that is not taken
+ * into the batch; *n_added = windows consumed; returns that window's StatusType (success if all were added). A window whose reads
+ * were all rejected is consumed like in the reference (it stays in the batch as an empty window): the call goes on and returns
+ * empty_poa_group at the end if no later window stopped it. */
 int gwb200_poa_batch_add_groups_flat(gwb200_poa_batch* batch, int32_t n_windows, const int32_t* win_nseq, const int32_t* seq_len,
                                      const char* seq_data, const int8_t* weights, int32_t* n_added);
 
@@ -236,7 +238,10 @@ int gwb200_aligner_create_with_allocator(gwb200_aligner** out, int32_t max_bandw
                                          gwb200_device_alloc_fn alloc_fn, gwb200_device_free_fn free_fn, void* user);
 void gwb200_aligner_destroy(gwb200_aligner* aligner);
 /* FixedBandAligner::add_alignment([max_bandwidth,] query, query_length, target, target_length, rc_query, rc_target)
- * -- aligner.hpp:96-97,158-170; aligner_global_myers_banded.cpp:155-258. max_bandwidth <= 0 => the aligner's own. */
+ * -- aligner.hpp:96-97,158-170; aligner_global_myers_banded.cpp:155-258. max_bandwidth == GWB200_ALN_DEFAULT_BANDWIDTH => the aligner's
+ * own (the overload without a bandwidth); any other value is taken as given: 0 is honoured (such a pair is skipped on the device
+ * and stays uninitialized, myers_gpu.cu:903-912), other negative values return generic_error, as in the reference. */
+#define GWB200_ALN_DEFAULT_BANDWIDTH (-2147483647 - 1)
 int gwb200_aligner_add_alignment(gwb200_aligner* aligner, int32_t max_bandwidth, const char* query, int32_t query_length,
                                  const char* target, int32_t target_length, int32_t reverse_complement_query,
                                  int32_t reverse_complement_target);

@@ -165,6 +165,17 @@ def test_aligner_api_contracts():
     r = al.get_alignments()
     assert r[0].status == cudaaligner.uninitialized and r[1].status == cudaaligner.success and r[1].convert_to_cigar() == "4M"
     al.close()
+    # an explicit bandwidth of 0 is honoured, not replaced by the aligner's own (aligner_global_myers_banded.cpp:160-178): the device
+    # skips such a pair (max_bandwidth - 1 < |t - q| for every non-empty pair, myers_gpu.cu:903-912); negative -> generic_error
+    al = cudaaligner.FixedBandAligner(64)
+    assert al.add_alignment("ACGTACGT", "ACGTACGT", max_bandwidth=0) == cudaaligner.success
+    assert al.add_alignment("ACGTACGT", "ACGTACGT") == cudaaligner.success
+    assert al.add_alignment("ACGT", "ACGT", max_bandwidth=-5) == cudaaligner.generic_error
+    al.align_all()
+    al.sync_alignments()
+    r = al.get_alignments()
+    assert r[0].status == cudaaligner.uninitialized and r[1].status == cudaaligner.success and r[1].convert_to_cigar() == "8M"
+    al.close()
     # pygenomeworks shim surface
     b = cudaaligner.CudaAlignerBatch(10, 10, 2)
     assert b.add_alignment("AAATC", "TACGTTTT") == 0

@@ -325,4 +325,15 @@ def test_empty_group_stays_in_the_batch_without_touching_other_windows():
         cons, cov, st = b.get_consensus()
         assert st == [0, cudapoa.empty_poa_group, 0, cudapoa.empty_poa_group], st
         assert cons[0] == good[0] and cons[2] == good[0] and cons[1] == "" and cons[3] == ""
+        # the flat entry consumes the empty window and goes on: the window <-> result mapping of the caller stays intact
+        b.reset()
+        groups = [good, ["A" * 1025], good]
+        win_nseq = np.array([len(g) for g in groups], dtype=np.int32)
+        seq_len = np.array([len(x) for g in groups for x in g], dtype=np.int32)
+        data = np.frombuffer(("".join(x for g in groups for x in g) + "\0").encode(), dtype=np.uint8)
+        rc, added = b.add_poa_groups_flat(win_nseq, seq_len, data)
+        assert rc == cudapoa.empty_poa_group and added == 3 and b.total_poas == 3
+        b.generate_poa()
+        cons, cov, st = b.get_consensus()
+        assert st == [0, cudapoa.empty_poa_group, 0] and cons[0] == good[0] and cons[2] == good[0]
         b.close()
