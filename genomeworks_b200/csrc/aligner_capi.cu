@@ -173,13 +173,23 @@ struct gwb200_aligner
 namespace
 {
 
+// Words per matrix (pv, mv, score) of one workspace. The three matrices of a workspace are contiguous; the skewed score pass
+// (myers_skew.cuh) lays its block records over all three and needs a little more than the reference's
+// n_words_band x (target + 1) per matrix when the band is the widest one allowed: an eighth of slack covers it (a pass whose
+// records do not fit runs the classic formulation instead).
+int64_t workspace_pitch(int64_t max_matrix)
+{
+    const int64_t ws = std::max<int64_t>(max_matrix, 1);
+    return (ws + ws / 8 + 1024 + 3) & ~3ll;
+}
+
 int64_t memory_requirement(const gwb200_aligner* a, int64_t max_matrix, int32_t max_query, int64_t seq_sum, int32_t n)
 {
     // same accounting shape as fits_device_memory (aligner_global_myers_banded.cpp:494-538): workspaces for every resident
     // CTA + sequences, result slots and per-alignment arrays
     const int64_t n_blocks = std::min<int64_t>(static_cast<int64_t>(a->n_sms) * kBlocksPerSM, std::max(n, 1));
     const int64_t qpat     = 4ll * ((max_query + 31) / 32);
-    int64_t req            = n_blocks * (max_matrix * 12 + qpat * 4);
+    int64_t req            = n_blocks * (workspace_pitch(max_matrix) * 12 + qpat * 4);
     req += seq_sum * (1 + 1 + 4 + 1 + 4); // sequences, slots (actions + runs), compacted (actions + runs)
     req += (2ll * n + 1) * 8 + n * (4 + 4 + 4 + 4 + 4) + 4096 * 16;
     return req;
@@ -351,7 +361,7 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     const int32_t n_blocks = static_cast<int32_t>(std::min<int64_t>(static_cast<int64_t>(a->n_sms) * kBlocksPerSM, n));
     const int32_t qpat_el  = 4 * ((a->max_query + 31) / 32) + 4;
     const int64_t ws       = std::max<int64_t>(a->max_matrix, 1);
-    const int64_t ws_pitch = (ws + 3) & ~3ll; // 16-byte aligned workspaces: the backtrace stages them by bulk copies
+    const int64_t ws_pitch = workspace_pitch(ws); // 16-byte aligned matrices: the backtrace stages them by bulk copies
     // a second workspace per CTA lets the pass of the doubled Ukkonen estimate run alongside the current one; only when the
     // budget the caller gave covers it (admission keeps counting one workspace per CTA, like the reference)
     bool speculate = true;
@@ -363,8 +373,8 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     bool ok = a->seq_d.ensure(seq_sum + 16) && a->seq_starts_d.ensure(2ll * n + 1) && a->max_bw_d.ensure(n) && a->sched_d.ensure(n) &&
               a->counter_d.ensure(1) && a->path_len_d.ensure(n) && a->offsets_d.ensure(n + 1) && a->metadata_d.ensure(n) &&
               a->slot_actions_d.ensure(seq_sum + 16) && a->slot_runs_d.ensure(seq_sum + 16) && a->actions_d.ensure(seq_sum + 16) &&
-              a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(ws_pitch * ws_count) && a->mv_d.ensure(ws_pitch * ws_count) &&
-              a->score_d.ensure(ws_pitch * ws_count) && a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
+              a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(3 * ws_pitch * ws_count) &&
+              a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
               a->offsets_h.ensure(n + 1, false) && a->metadata_h.ensure(n, false) && a->cells_h.ensure(1, false);
     if (!ok)
         return set_error(GWB200_E_RUNTIME, "Out of memory.");
@@ -391,12 +401,17 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     P.sched_index   = a->sched_d.p;
     P.sched_counter = a->counter_d.p;
     P.n_alignments  = n;
+    // one buffer: workspace k = [pv | mv | score] at 3 * ws_pitch * k
     P.pv            = a->pv_d.p;
-    P.mv            = a->mv_d.p;
-    P.score         = a->score_d.p;
+    P.mv            = a->pv_d.p + ws_pitch;
+    P.score         = reinterpret_cast<int32_t*>(a->pv_d.p + 2 * ws_pitch);
     P.ws_elems      = ws;
-    P.ws_stride     = ws_pitch;
+    P.ws_stride     = 3 * ws_pitch;
+    P.ws_phys       = 3 * ws_pitch;
     P.speculate     = speculate ? 1 : 0;
+    P.skew          = 1;
+    if (const char* e = std::getenv("GWB200_MYERS_SKEW")) // development A/B switch: 0 = classic score passes only
+        P.skew = std::atoi(e) != 0 ? 1 : 0;
     P.qpat          = a->qpat_d.p;
     P.qpat_elems    = qpat_el;
     P.slot_actions  = a->slot_actions_d.p;

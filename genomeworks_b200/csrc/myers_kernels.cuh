@@ -15,6 +15,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "myers_skew.cuh"
+
 namespace gwb200
 {
 namespace myers
@@ -27,6 +29,12 @@ constexpr int32_t kStageStride = 33; // words per staged column (+1: lanes that 
 constexpr int32_t kQpatSmemWords = 320; // queries of up to 10 240 bases keep their bit patterns in shared memory
 constexpr uint32_t kFull      = 0xffffffffu;
 constexpr int32_t kOutOfBand  = INT32_MAX - 1; // myers_gpu.cu:448
+// skewed score pass (myers_skew.cuh): what its shared-memory tables hold
+constexpr int32_t kSkewMaxColumns = 16384;                   // target columns (2-bit codes, 16 per word)
+constexpr int32_t kSkewTgtWords   = kSkewMaxColumns / 16 + 2;
+constexpr int32_t kSkewQ64Stride  = kQpatSmemWords / 2 + 2;  // 64-bit pattern words per character
+constexpr int32_t kSkewStageCols  = 32;
+constexpr int32_t kSkewStageBlocks = 3;
 
 enum : int8_t
 {
@@ -50,7 +58,9 @@ struct DeviceParams
     int32_t* score;
     int64_t ws_elems;            // elements per CTA in pv / mv / score
     int64_t ws_stride;           // distance between workspaces (ws_elems rounded up to 4 elements: 16-byte aligned)
+    int64_t ws_phys;             // 32-bit words one workspace really holds from its pv pointer on (pv | mv | score are contiguous)
     int32_t speculate;           // 1: two workspaces per CTA, the pass of the doubled estimate runs alongside (see the kernel)
+    int32_t skew;                // 1: bands of >= 128 rows run the skewed score pass (myers_skew.cuh); 0: classic passes only (A/B)
     WordType* qpat;
     int32_t qpat_elems;          // elements per CTA (>= 4 * ceil(max_query/32))
     // per-alignment result slots: alignment i owns [seq_starts[2i], seq_starts[2i+2])
@@ -386,25 +396,17 @@ __device__ void diagonal_general(int32_t lane, const View<WordType>& pvm, const 
     }
 }
 
+__device__ __forceinline__ void band_phases(int32_t band_width, int32_t query_size, int32_t target_size, int32_t p, int32_t& diagonal_begin,
+                                            int32_t& diagonal_end);
+
 // myers_compute_scores_edit_dist_banded, myers_gpu.cu:753-846
 __device__ void compute_scores_banded(int32_t lane, int32_t& diagonal_begin, int32_t& diagonal_end, const View<WordType>& pvm,
                                       const View<WordType>& mvm, const View<int32_t>& scm, const QPat& Q, const WordType* qpat, int32_t n_words_query,
                                       const char* target, int32_t target_size, int32_t query_size, int32_t band_width, int32_t n_words_band,
                                       int32_t p)
 {
-    int32_t sym = 0;
     const bool full_myers = band_width >= query_size;
-    if (full_myers)
-    {
-        diagonal_begin = target_size + 1;
-        diagonal_end   = target_size + 1;
-    }
-    else
-    {
-        sym            = (band_width - min(1 + 2 * p + abs(target_size - query_size), query_size) == 0) ? 1 : 0;
-        diagonal_begin = query_size < target_size ? target_size - query_size + p + 2 : p + 2 + (1 - sym);
-        diagonal_end   = query_size < target_size ? query_size - p + sym : query_size - (query_size - target_size) - p + 1;
-    }
+    band_phases(band_width, query_size, target_size, p, diagonal_begin, diagonal_end);
     if (n_words_band <= 32)
     {
         if (lane < n_words_band)
@@ -452,6 +454,158 @@ __device__ void compute_scores_banded(int32_t lane, int32_t& diagonal_begin, int
     }
 }
 
+// diagonal_begin / diagonal_end of a pass (myers_gpu.cu:826-840), shared by the two formulations of the score pass
+__device__ __forceinline__ void band_phases(int32_t band_width, int32_t query_size, int32_t target_size, int32_t p, int32_t& diagonal_begin,
+                                            int32_t& diagonal_end)
+{
+    if (band_width >= query_size)
+    {
+        diagonal_begin = target_size + 1;
+        diagonal_end   = target_size + 1;
+        return;
+    }
+    const int32_t sym = (band_width - min(1 + 2 * p + abs(target_size - query_size), query_size) == 0) ? 1 : 0;
+    diagonal_begin    = query_size < target_size ? target_size - query_size + p + 2 : p + 2 + (1 - sym);
+    diagonal_end      = query_size < target_size ? query_size - p + sym : query_size - (query_size - target_size) - p + 1;
+}
+
+// ---- skewed score pass: lane = 64-row block of the query, K columns per step (all arithmetic in myers_skew.cuh)
+// rec: the pass's records ([step][chunk][lane] in 16-byte units); s_q64: [4][kSkewQ64Stride] 64-bit query patterns;
+// s_tgt: 2-bit pattern index of target[t - 1] at position t
+__device__ void compute_scores_skew(int32_t lane, const skew::Geom& g, uint4* __restrict__ rec, const uint64_t* s_q64, const uint32_t* s_tgt)
+{
+    if (lane < g.nbl)
+    {
+        const uint32_t mask = g.nbl == 32 ? kFull : ((1u << g.nbl) - 1u);
+        const int32_t up    = (lane + g.nbl - 1) % g.nbl;
+        skew::LaneState L;
+        skew::lane_init(L, lane);
+        skew::Link mine;
+        mine.hbits = 0;
+        mine.S0    = 0;
+        uint4* dst = rec + lane;
+        for (int32_t s = 0; s < g.n_steps; ++s, dst += skew::kChunks * g.nbl)
+        {
+            // what the lane above produced in the previous step: the same batch of its block
+            skew::Link in;
+            in.hbits   = __shfl_sync(mask, mine.hbits, up);
+            in.S0      = __shfl_sync(mask, mine.S0, up);
+            int32_t cb = s - L.B;
+            if (L.B <= g.last_block && cb >= 0 && cb < g.n_batches && skew::block_retired(g, L.B, cb))
+            {
+                skew::lane_init(L, L.B + g.nbl); // the band has left the block: on to the next block of this lane
+                cb = s - L.B;
+            }
+            if (L.B <= g.last_block && cb >= 0 && cb < g.n_batches)
+            {
+                const int32_t t0  = skew::kK * cb;
+                const uint32_t tw = s_tgt[t0 >> 4] >> ((t0 & 15) * 2);
+                uint64_t eqs[skew::kK];
+#pragma unroll
+                for (int32_t k = 0; k < skew::kK; k++)
+                    eqs[k] = s_q64[((tw >> (2 * k)) & 3u) * kSkewQ64Stride + L.B];
+                uint64_t pm[skew::kK][2];
+                int32_t sc[skew::kK];
+                mine = skew::lane_step(g, L, cb, eqs, in, pm, sc);
+#pragma unroll
+                for (int32_t k = 0; k < skew::kK; k++)
+                    dst[k * g.nbl] = make_uint4(static_cast<uint32_t>(pm[k][0]), static_cast<uint32_t>(pm[k][0] >> 32), static_cast<uint32_t>(pm[k][1]),
+                                                static_cast<uint32_t>(pm[k][1] >> 32));
+#pragma unroll
+                for (int32_t k = 0; k < skew::kK; k += 4)
+                    dst[(skew::kK + k / 4) * g.nbl] = make_uint4(static_cast<uint32_t>(sc[k]), static_cast<uint32_t>(sc[k + 1]),
+                                                                 static_cast<uint32_t>(sc[k + 2]), static_cast<uint32_t>(sc[k + 3]));
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// score_at() straight from the records in global memory
+struct SkewGlobalLoader
+{
+    const uint4* rec;
+    const skew::Geom* g;
+    __device__ __forceinline__ void pvmv(int32_t B, int32_t j, uint64_t& pv, uint64_t& mv) const
+    {
+        const uint4 v = rec[skew::chunk_index(*g, B, j, j % skew::kK)];
+        pv            = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
+        mv            = static_cast<uint64_t>(v.z) | (static_cast<uint64_t>(v.w) << 32);
+    }
+    __device__ __forceinline__ int32_t S(int32_t B, int32_t j) const
+    {
+        const int32_t* c = reinterpret_cast<const int32_t*>(rec + skew::chunk_index(*g, B, j, skew::kK + (j % skew::kK) / 4));
+        return c[(j % skew::kK) % 4];
+    }
+};
+
+// Backtrace accessor on the block records: 32 columns x 3 blocks around the walk in shared memory (the walk only moves up and
+// to the left: within 32 columns it stays inside two blocks, the third serves the scores taken from the block above)
+struct SkewStage
+{
+    skew::Geom g;
+    const uint4* rec;
+    uint4* s_pm;  // [kSkewStageBlocks][kSkewStageCols] {pv, mv}
+    int32_t* s_S; // [kSkewStageBlocks][kSkewStageCols]
+    int32_t jlo, jhi; // staged columns [jlo, jhi]; jhi < jlo => nothing staged
+    int32_t bhi;      // staged blocks [bhi - 2, bhi]
+    static constexpr bool use_smem = true;
+
+    __device__ __forceinline__ bool need(int32_t i, int32_t j) const
+    {
+        if (jhi < jlo || j - 1 < jlo || j > jhi)
+            return true;
+        const int32_t r = g.top(j) + i - 1;
+        return (r >> 6) > bhi || (bhi > 2 && r - 34 < 64 * (bhi - 2));
+    }
+    __device__ __forceinline__ void refill(int32_t i, int32_t j, int32_t lane)
+    {
+        __syncwarp();
+        jhi             = j;
+        jlo             = max(0, j - kSkewStageCols + 1);
+        const int32_t r = max(0, g.top(j) + i - 1);
+        bhi             = min(r >> 6, g.last_block);
+        const int32_t c = jlo + lane;
+        if (c <= jhi)
+        {
+#pragma unroll
+            for (int32_t b = 0; b < kSkewStageBlocks; b++)
+            {
+                const int32_t B = bhi - (kSkewStageBlocks - 1) + b;
+                if (B >= 0)
+                {
+                    s_pm[b * kSkewStageCols + lane] = rec[skew::chunk_index(g, B, c, c % skew::kK)];
+                    s_S[b * kSkewStageCols + lane] =
+                        reinterpret_cast<const int32_t*>(rec + skew::chunk_index(g, B, c, skew::kK + (c % skew::kK) / 4))[(c % skew::kK) % 4];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // loader interface of skew::score_at; anything outside the stage comes from global memory (never wrong, only slower)
+    __device__ __forceinline__ void pvmv(int32_t B, int32_t j, uint64_t& pv, uint64_t& mv) const
+    {
+        const int32_t b = B - (bhi - (kSkewStageBlocks - 1));
+        uint4 v;
+        if (b >= 0 && b < kSkewStageBlocks && j >= jlo && j <= jhi)
+            v = s_pm[b * kSkewStageCols + (j - jlo)];
+        else
+            v = rec[skew::chunk_index(g, B, j, j % skew::kK)];
+        pv = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
+        mv = static_cast<uint64_t>(v.z) | (static_cast<uint64_t>(v.w) << 32);
+    }
+    __device__ __forceinline__ int32_t S(int32_t B, int32_t j) const
+    {
+        const int32_t b = B - (bhi - (kSkewStageBlocks - 1));
+        if (b >= 0 && b < kSkewStageBlocks && j >= jlo && j <= jhi)
+            return s_S[b * kSkewStageCols + (j - jlo)];
+        return reinterpret_cast<const int32_t*>(rec + skew::chunk_index(g, B, j, skew::kK + (j % skew::kK) / 4))[(j % skew::kK) % 4];
+    }
+    __device__ __forceinline__ int32_t get(int32_t i, int32_t j) const { return skew::score_at(g, i, j, *this); }
+    __device__ __forceinline__ int32_t first_score(int32_t i, int32_t j) const { return get(i, j); }
+    __device__ __forceinline__ void set_band(int32_t) {}
+};
+
 // Accessor for the backtrace: either the shared-memory stage (bands of <= 32 words) or global memory.
 struct Stage
 {
@@ -469,7 +623,13 @@ struct Stage
     bool use_smem;
     WordType last_entry_mask;
 
-    __device__ __forceinline__ void refill(int32_t j, int32_t lane)
+    __device__ __forceinline__ bool need(int32_t, int32_t j) const { return use_smem && j - 1 < jlo; }
+    __device__ __forceinline__ int32_t first_score(int32_t i, int32_t j) const { return scm((i - 1) / kWord, j); }
+    __device__ __forceinline__ void set_band(int32_t band_width)
+    {
+        last_entry_mask = band_width % kWord != 0 ? (WordType(1) << (band_width % kWord)) - 1 : ~WordType(0);
+    }
+    __device__ __forceinline__ void refill(int32_t, int32_t j, int32_t lane)
     {
         // make columns [j - kStageCols + 1, j] resident (clamped at 0). The staged block is one contiguous piece of each
         // column-major matrix (n_words_band words per column): with a multiple of 4 words per column it is fetched by three
@@ -587,28 +747,29 @@ __device__ __forceinline__ void rle_append_diagonal_run(RleWriter& W, uint32_t m
 
 // myers_backtrace_banded, myers_gpu.cu:444-627. All lanes walk redundantly (warp-uniform control flow) on staged data;
 // lane 0 writes the RLE path. Returns the number of RLE entries.
-__device__ int32_t backtrace_banded(int32_t lane, Stage& S, int8_t* path, int32_t* path_count, int32_t diagonal_begin, int32_t diagonal_end,
+template <typename StageT>
+__device__ int32_t backtrace_banded(int32_t lane, StageT& S, int8_t* path, int32_t* path_count, int32_t diagonal_begin, int32_t diagonal_end,
                                     int32_t band_width, int32_t target_size)
 {
     int32_t i = band_width;
     int32_t j = target_size;
-    S.last_entry_mask = band_width % kWord != 0 ? (WordType(1) << (band_width % kWord)) - 1 : ~WordType(0);
+    S.set_band(band_width);
     int32_t last_diagonal_score = kOutOfBand;
     if (diagonal_end >= 2)
     {
         if (S.use_smem)
-            S.refill(diagonal_end - 2, lane);
+            S.refill(1, diagonal_end - 2, lane);
         last_diagonal_score = S.get(1, diagonal_end - 2) + 2;
     }
     if (S.use_smem)
-        S.refill(j, lane);
-    int32_t myscore = i > 0 ? S.scm((i - 1) / kWord, j) : 0;
+        S.refill(i, j, lane);
+    int32_t myscore = i > 0 ? S.first_score(i, j) : 0;
     RleWriter W{path, path_count, 0, -1, 0, lane == 0};
 
     while (j >= diagonal_end)
     {
-        if (S.use_smem && j - 1 < S.jlo && j >= 1)
-            S.refill(j, lane);
+        if (S.need(i, j) && j >= 1)
+            S.refill(i, j, lane);
         int32_t r;
         const int32_t above = i <= 1 ? (last_diagonal_score + j - diagonal_end) : S.get(i - 1, j);
         const int32_t diag  = i <= 1 ? (last_diagonal_score + j - 1 - diagonal_end) : S.get(i - 1, j - 1);
@@ -637,8 +798,8 @@ __device__ int32_t backtrace_banded(int32_t lane, Stage& S, int8_t* path, int32_
     }
     while (j >= diagonal_begin)
     {
-        if (S.use_smem && j - 1 < S.jlo && j >= 1)
-            S.refill(j, lane);
+        if (S.need(i, j) && j >= 1)
+            S.refill(i, j, lane);
         if (S.use_smem && i >= 1)
         {
             // speculative run of diagonal steps (band row i fixed, j decreasing): lane k evaluates the step at column j - k on the
@@ -695,8 +856,8 @@ __device__ int32_t backtrace_banded(int32_t lane, Stage& S, int8_t* path, int32_
     }
     while (i > 0 && j > 0)
     {
-        if (S.use_smem && j - 1 < S.jlo)
-            S.refill(j, lane);
+        if (S.need(i, j))
+            S.refill(i, j, lane);
         if (S.use_smem && i <= band_width)
         {
             // speculative run of diagonal steps in the top-left block: lane k evaluates the step at (i - k, j - k)
@@ -823,10 +984,25 @@ __device__ __forceinline__ PassPlan plan_pass(int32_t k, int32_t query_size, int
 // not have reached is dropped and not counted in the executed cells. The warp that owns the final pass does the backtrace.
 __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams P)
 {
-    __shared__ __align__(16) WordType s_pv[kStageCols * kStageStride + 8];
-    __shared__ __align__(16) WordType s_mv[kStageCols * kStageStride + 8];
-    __shared__ __align__(16) int32_t s_sc[kStageCols * kStageStride + 8];
+    // one buffer, carved per formulation: the classic backtrace stage (pv | mv | score, 32 columns x 32 words), or the skewed
+    // pass's tables (64-bit query patterns, 2-bit target codes) followed by its backtrace stage. A backtrace never runs while
+    // a score pass of the same CTA is running, and the tables are rebuilt for every alignment.
+    constexpr int32_t kStageWords   = kStageCols * kStageStride + 8;
+    constexpr int32_t kSkewQ64Words = 4 * kSkewQ64Stride * 2;
+    constexpr int32_t kSkewPmOff    = (kSkewQ64Words + kSkewTgtWords + 3) & ~3;
+    constexpr int32_t kSkewSOff     = kSkewPmOff + kSkewStageBlocks * kSkewStageCols * 4;
+    constexpr int32_t kSkewWords    = kSkewSOff + kSkewStageBlocks * kSkewStageCols;
+    constexpr int32_t kRawWords     = (3 * kStageWords > kSkewWords ? 3 * kStageWords : kSkewWords);
+    __shared__ __align__(16) WordType s_raw[kRawWords];
+    WordType* const s_pv   = s_raw;
+    WordType* const s_mv   = s_raw + kStageWords;
+    int32_t* const s_sc    = reinterpret_cast<int32_t*>(s_raw + 2 * kStageWords);
+    uint64_t* const s_q64  = reinterpret_cast<uint64_t*>(s_raw);
+    uint32_t* const s_tgt  = s_raw + kSkewQ64Words;
+    uint4* const s_skpm    = reinterpret_cast<uint4*>(s_raw + kSkewPmOff);
+    int32_t* const s_skS   = reinterpret_cast<int32_t*>(s_raw + kSkewSOff);
     __shared__ __align__(16) WordType s_qpat[4 * (kQpatSmemWords + 1)];
+    __shared__ int32_t s_skew[2];
     __shared__ unsigned long long s_bar;
     __shared__ uint32_t s_phase;
     __shared__ int32_t s_task;
@@ -927,6 +1103,32 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
             s_qpat[threadIdx.x * (n_words + 1) + n_words] = 0;
         __threadfence_block();
         __syncthreads();
+        // tables of the skewed pass: 64-bit patterns from the 32-bit ones (the padding word is the upper half of an odd last
+        // block), 2-bit pattern index of target[t - 1] at position t
+        const bool skew_tables = P.skew != 0 && n_words <= kQpatSmemWords && target_size + 1 + skew::kK <= kSkewMaxColumns;
+        if (skew_tables)
+        {
+            const int32_t nb64 = (n_words + 1) / 2;
+            for (int32_t e = threadIdx.x; e < 4 * nb64; e += 64)
+            {
+                const int32_t c = e / nb64, b = e - c * nb64;
+                const WordType* col = s_qpat + c * (n_words + 1);
+                s_q64[c * kSkewQ64Stride + b] = static_cast<uint64_t>(col[2 * b]) | (static_cast<uint64_t>(col[2 * b + 1]) << 32);
+            }
+            const int32_t n_tw = (target_size + 1 + skew::kK + 15) / 16 + 1;
+            for (int32_t w = threadIdx.x; w < n_tw; w += 64)
+            {
+                uint32_t v = 0;
+                for (int32_t k = 0; k < 16; k++)
+                {
+                    const int32_t t = 16 * w + k;
+                    if (t >= 1 && t <= target_size)
+                        v |= static_cast<uint32_t>((target[t - 1] >> 1) & 0x3) << (2 * k);
+                }
+                s_tgt[w] = v;
+            }
+        }
+        __syncthreads();
         QPat Q;
         Q.sbase   = n_words <= kQpatSmemWords ? smem_addr(s_qpat) : 0u;
         Q.gbase   = qpat;
@@ -953,13 +1155,31 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
                 mvm.rows = M.n_words_band;
                 scm.rows = M.n_words_band;
                 int32_t db = -1, de = -1;
-                compute_scores_banded(lane, db, de, pvm, mvm, scm, Q, qpat, n_words, target, target_size, query_size, M.band_width, M.n_words_band, M.p);
-                __syncwarp();
+                band_phases(M.band_width, query_size, target_size, M.p, db, de);
+                const skew::Geom G  = skew::make_geom(M.band_width, query_size, target_size, db);
+                const bool use_skew = skew_tables && skew::usable(G) && skew::words_needed(G) <= P.ws_phys;
+                int32_t dist;
+                if (use_skew)
+                {
+                    uint4* rec = reinterpret_cast<uint4*>(pv_ws);
+                    compute_scores_skew(lane, G, rec, s_q64, s_tgt);
+                    __threadfence_block();
+                    const SkewGlobalLoader ld{rec, &G};
+                    dist = skew::score_at(G, M.band_width, target_size, ld);
+                }
+                else
+                {
+                    compute_scores_banded(lane, db, de, pvm, mvm, scm, Q, qpat, n_words, target, target_size, query_size, M.band_width, M.n_words_band,
+                                          M.p);
+                    __syncwarp();
+                    dist = M.n_words_band > 0 ? scm(M.n_words_band - 1, target_size) : target_size;
+                }
                 if (lane == 0)
                 {
-                    s_dist[warp] = M.n_words_band > 0 ? scm(M.n_words_band - 1, target_size) : target_size;
+                    s_dist[warp] = dist;
                     s_dbeg[warp] = db;
                     s_dend[warp] = de;
+                    s_skew[warp] = use_skew ? 1 : 0;
                 }
             }
             __syncthreads();
@@ -1031,6 +1251,20 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
                 pvm.rows          = nwb;
                 mvm.rows          = nwb;
                 scm.rows          = nwb;
+                if (s_skew[warp] != 0)
+                {
+                    SkewStage K;
+                    K.g    = skew::make_geom(bw, query_size, target_size, s_dbeg[warp]);
+                    K.rec  = reinterpret_cast<const uint4*>(pv_ws);
+                    K.s_pm = s_skpm;
+                    K.s_S  = s_skS;
+                    K.jlo  = 0;
+                    K.jhi  = -1;
+                    K.bhi  = 0;
+                    path_length = backtrace_banded(lane, K, out_actions, out_runs, s_dbeg[warp], s_dend[warp], bw, target_size);
+                }
+                else
+                {
                 Stage S;
                 S.s_pv         = s_pv;
                 S.s_mv         = s_mv;
@@ -1049,6 +1283,7 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
                 path_length    = backtrace_banded(lane, S, out_actions, out_runs, s_dbeg[warp], s_dend[warp], bw, target_size);
                 if (lane == 0)
                     s_phase = S.phase;
+                }
             }
             if (lane == 0)
             {

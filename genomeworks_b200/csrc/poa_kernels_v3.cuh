@@ -97,11 +97,17 @@ struct V3Shared
     uint32_t pad_[2];
 };
 
+#ifndef GWB200_V3_CPL32
+#define GWB200_V3_CPL32 8 // 4: one 16-byte unit per lane and chunk (the round-2 layout, kept as the A/B partner)
+#endif
+
 template <typename ScoreT>
 struct V3Cells
 {
-    static constexpr int32_t kCPL   = 16 / static_cast<int32_t>(sizeof(ScoreT)); // cells per lane and chunk (one 16-byte unit)
-    static constexpr int32_t kChunk = 32 * kCPL;                                 // columns per chunk
+    // cells per lane and chunk: 8 (int16: one 16-byte unit, int32: two), so that the per-chunk costs -- neighbour shuffle, carry
+    // shuffles and ballot, addressing, band tests -- are paid once per 256 columns
+    static constexpr int32_t kCPL   = sizeof(ScoreT) == 2 ? 8 : GWB200_V3_CPL32;
+    static constexpr int32_t kChunk = 32 * kCPL; // columns per chunk
 };
 
 // 16-byte unit <-> CPL int32 values
@@ -115,6 +121,14 @@ __device__ __forceinline__ void unit_load(const ScoreT* p, int32_t* b)
         b[1]         = v.y;
         b[2]         = v.z;
         b[3]         = v.w;
+        if constexpr (CPL == 8)
+        {
+            const int4 u = *reinterpret_cast<const int4*>(p + 4);
+            b[4]         = u.x;
+            b[5]         = u.y;
+            b[6]         = u.z;
+            b[7]         = u.w;
+        }
     }
     else
     {
@@ -139,6 +153,8 @@ __device__ __forceinline__ void unit_store(ScoreT* p, int32_t left, const int32_
     if constexpr (sizeof(ScoreT) == 4)
     {
         *reinterpret_cast<int4*>(p) = make_int4(left, s[0], s[1], s[2]);
+        if constexpr (CPL == 8)
+            *reinterpret_cast<int4*>(p + 4) = make_int4(s[3], s[4], s[5], s[6]);
     }
     else
     {
@@ -217,6 +233,7 @@ struct RowCtx
     ScoreT* grow;        // second copy in global memory (lane stores instead of the bulk copy), or nullptr
     int32_t sh0, lim0, sh1, lim1;
     int32_t base, bw, gap, match, mismatch;
+    uint32_t base4; // the row's base in every byte
 };
 
 // NJ consecutive chunks of one row, starting at chunk c0 (all of them exist: c0 + NJ <= number of chunks). Straight-line code:
@@ -245,23 +262,16 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
             act[j]            = off < cx.bw;
 #pragma unroll
             for (int32_t h = 0; h < CPL / 4; h++)
-                w[j][h] = __ldg(reinterpret_cast<const uint32_t*>(cx.rd + off + 4 * h));
+                w[j][h] = __ldg(reinterpret_cast<const uint32_t*>(cx.rd + off + 4 * h)) ^ cx.base4;
             const int32_t o = cx.sh0 + off;
             in0[j]          = act[j] && o <= cx.lim0;
-#pragma unroll
-            for (int32_t i = 0; i < CPL; i++)
-                b0[j][i] = kMin;
-            if (in0[j])
-                unit_load<ScoreT, CPL>(cx.prow0 + o, b0[j]);
+            // lanes outside the predecessor's band load its first unit instead: their values are discarded by ok0 below
+            unit_load<ScoreT, CPL>(cx.prow0 + (in0[j] ? o : 0), b0[j]);
             if (TWO)
             {
                 const int32_t o1 = cx.sh1 + off;
                 in1[j]           = act[j] && o1 <= cx.lim1;
-#pragma unroll
-                for (int32_t i = 0; i < CPL; i++)
-                    b1[j][i] = kMin;
-                if (in1[j])
-                    unit_load<ScoreT, CPL>(cx.prow1 + o1, b1[j]);
+                unit_load<ScoreT, CPL>(cx.prow1 + (in1[j] ? o1 : 0), b1[j]);
             }
         }
         // ---- the value right of each unit: first value of the right neighbour's unit, or an own load at the band / chunk edge
@@ -295,8 +305,8 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
 #pragma unroll
             for (int32_t i = 0; i < CPL; i++)
             {
-                const int32_t ch = static_cast<int32_t>((w[j][i >> 2] >> (8 * (i & 3))) & 0xffu);
-                const int32_t q  = (cx.base == ch) ? cx.match : cx.mismatch;
+                // w holds read ^ base in every byte: a zero byte is a match (one logic op with a predicate result per cell)
+                const int32_t q  = ((w[j][i >> 2] & (0xffu << (8 * (i & 3)))) == 0u) ? cx.match : cx.mismatch;
                 const bool ok0   = (i < 4) ? in0[j] : (in0[j] && (cx.sh0 + off + 4) <= cx.lim0);
                 const int32_t t0 = static_cast<ScoreT>(__viaddmax_s32(b0[j][i + 1], gap, b0[j][i] + q));
                 int32_t v        = ok0 ? t0 : kMin;
@@ -528,6 +538,7 @@ __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const
                 cx.sh1   = sh1;
                 cx.lim1  = lim1;
                 cx.base  = base;
+                cx.base4 = static_cast<uint32_t>(base) * 0x01010101u;
                 cx.bw    = band_width;
                 cx.gap   = gap;
                 cx.match = match;

@@ -567,4 +567,43 @@ int32_t oracle_myers_banded_align(const char* query, int32_t query_length, const
     return static_cast<int32_t>(r.actions.size());
 }
 
+// Every cell of one band pass (for checking other formulations of the same band, tests/cpp/myers_skew_model.cpp):
+// out[(i - 1) + band_width * j] = get_myers_score(i, j) for i = 1 .. band_width, j = 0 .. target_length.
+int32_t oracle_myers_band_scores(const char* query, int32_t query_length, const char* target, int32_t target_length, int32_t band_width,
+                                 int32_t p, int32_t* out, int32_t* diagonal_begin, int32_t* diagonal_end)
+{
+    Problem P;
+    P.query       = query;
+    P.target      = target;
+    P.query_size  = query_length;
+    P.target_size = target_length;
+    const int32_t n_words = ceiling_divide(query_length, word_size);
+    P.qp.reshape(n_words, 4);
+    const char chars[4] = {'A', 'C', 'T', 'G'};
+    for (int32_t idx = 0; idx < n_words; idx++)
+        for (int32_t c = 0; c < 4; c++)
+        {
+            const int32_t offset = idx * word_size;
+            const int32_t max_i  = std::min(query_length - offset, word_size);
+            WordType r           = 0;
+            for (int32_t i = 0; i < max_i; ++i)
+                if (chars[c] == query[i + offset])
+                    r |= (WordType(1) << i);
+            P.qp(idx, c) = r;
+        }
+    const int32_t n_words_band = ceiling_divide(band_width, word_size);
+    P.pv.reshape(n_words_band, target_length + 1);
+    P.mv.reshape(n_words_band, target_length + 1);
+    P.score.reshape(n_words_band, target_length + 1);
+    int32_t db = -1, de = -1;
+    compute_scores_banded(P, db, de, band_width, n_words_band, p);
+    *diagonal_begin = db;
+    *diagonal_end   = de;
+    const WordType last_entry_mask = band_width % word_size != 0 ? (WordType(1) << (band_width % word_size)) - 1 : ~WordType(0);
+    for (int32_t j = 0; j <= target_length; j++)
+        for (int32_t i = 1; i <= band_width; i++)
+            out[(i - 1) + static_cast<int64_t>(band_width) * j] = get_myers_score(i, j, P, last_entry_mask);
+    return 0;
+}
+
 } // extern "C"
