@@ -374,8 +374,8 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
               a->counter_d.ensure(1) && a->path_len_d.ensure(n) && a->offsets_d.ensure(n + 1) && a->metadata_d.ensure(n) &&
               a->slot_actions_d.ensure(seq_sum + 16) && a->slot_runs_d.ensure(seq_sum + 16) && a->actions_d.ensure(seq_sum + 16) &&
               a->runs_d.ensure(seq_sum + 16) && a->pv_d.ensure(3 * ws_pitch * ws_count) &&
-              a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(1) &&
-              a->offsets_h.ensure(n + 1, false) && a->metadata_h.ensure(n, false) && a->cells_h.ensure(1, false);
+              a->qpat_d.ensure(static_cast<int64_t>(qpat_el) * n_blocks) && a->cells_d.ensure(8) &&
+              a->offsets_h.ensure(n + 1, false) && a->metadata_h.ensure(n, false) && a->cells_h.ensure(8, false);
     if (!ok)
         return set_error(GWB200_E_RUNTIME, "Out of memory.");
 
@@ -390,7 +390,7 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     GWB200_CUDA_TRY(cudaMemcpyAsync(a->max_bw_d.p, a->max_bw_h.data(), 4ll * n, cudaMemcpyHostToDevice, a->stream));
     GWB200_CUDA_TRY(cudaMemcpyAsync(a->sched_d.p, sched.data(), 4ll * n, cudaMemcpyHostToDevice, a->stream));
     GWB200_CUDA_TRY(cudaMemsetAsync(a->counter_d.p, 0, 4, a->stream));
-    GWB200_CUDA_TRY(cudaMemsetAsync(a->cells_d.p, 0, 8, a->stream));
+    GWB200_CUDA_TRY(cudaMemsetAsync(a->cells_d.p, 0, 8 * 8, a->stream));
     // the host vectors above are pageable: make sure the copies have consumed them before they go out of scope
     GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream));
 
@@ -419,6 +419,7 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     P.path_len      = a->path_len_d.p;
     P.metadata      = a->metadata_d.p;
     P.cells         = a->cells_d.p;
+    P.timers        = std::getenv("GWB200_MYERS_TIMERS") ? a->cells_d.p + 4 : nullptr; // development: phase cycles, printed by sync
 
     // residency (kBlocksPerSM) assumes the full shared-memory carve-out regardless of any device-wide cache preference
     cudaFuncSetAttribute(myers_banded_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -431,7 +432,7 @@ int gwb200_aligner_align_all(gwb200_aligner* a)
     GWB200_CUDA_TRY(cudaEventRecord(a->ev1, a->stream));
     GWB200_CUDA_TRY(cudaMemcpyAsync(a->offsets_h.p, a->offsets_d.p, 4ll * (n + 1), cudaMemcpyDeviceToHost, a->stream));
     GWB200_CUDA_TRY(cudaMemcpyAsync(a->metadata_h.p, a->metadata_d.p, 4ll * n, cudaMemcpyDeviceToHost, a->stream));
-    GWB200_CUDA_TRY(cudaMemcpyAsync(a->cells_h.p, a->cells_d.p, 8, cudaMemcpyDeviceToHost, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->cells_h.p, a->cells_d.p, 8 * 8, cudaMemcpyDeviceToHost, a->stream));
     a->n_launched = n;
     a->aligned    = true;
     a->synced     = false;
@@ -456,6 +457,12 @@ int gwb200_aligner_sync_alignments(gwb200_aligner* a)
     GWB200_CUDA_TRY(cudaStreamSynchronize(a->stream)); // offsets + metadata are on the host now
     const int64_t total = a->offsets_h.p[n];
     a->total_len        = total;
+    if (std::getenv("GWB200_MYERS_TIMERS") && a->cells_h.p[7] != 0)
+    {
+        const double k = 1.0 / static_cast<double>(a->cells_h.p[7]);
+        std::fprintf(stderr, "gwb200 myers timers: %llu alignments, cycles per alignment: patterns %.0f, score passes %.0f, backtrace %.0f\n",
+                     a->cells_h.p[7], a->cells_h.p[4] * k, a->cells_h.p[5] * k, a->cells_h.p[6] * k);
+    }
     if (!a->actions_h.ensure(total + 16, false) || !a->runs_h.ensure(total + 16, false))
         return set_error(GWB200_E_RUNTIME, "Out of memory.");
     if (total > 0)
@@ -870,7 +877,7 @@ int gwb200_global_aligner_align_all(gwb200_global_aligner* a)
     GWB200_CUDA_TRY(cudaGetLastError());
     GWB200_CUDA_TRY(cudaMemcpyAsync(a->res_h.p, a->res_d.p, static_cast<int64_t>(a->max_result_length) * n, cudaMemcpyDeviceToHost, a->stream));
     GWB200_CUDA_TRY(cudaMemcpyAsync(a->res_len_h.p, a->res_len_d.p, 4ll * n, cudaMemcpyDeviceToHost, a->stream));
-    GWB200_CUDA_TRY(cudaMemcpyAsync(a->cells_h.p, a->cells_d.p, 8, cudaMemcpyDeviceToHost, a->stream));
+    GWB200_CUDA_TRY(cudaMemcpyAsync(a->cells_h.p, a->cells_d.p, 8 * 8, cudaMemcpyDeviceToHost, a->stream));
     a->n_launched = n;
     a->aligned    = true;
     a->synced     = false;

@@ -34,7 +34,7 @@ constexpr int32_t kSkewMaxColumns = 16384;                   // target columns (
 constexpr int32_t kSkewTgtWords   = kSkewMaxColumns / 16 + 2;
 constexpr int32_t kSkewQ64Stride  = kQpatSmemWords / 2 + 2;  // 64-bit pattern words per character
 constexpr int32_t kSkewStageCols  = 32;
-constexpr int32_t kSkewStageBlocks = 3;
+constexpr int32_t kSkewStageBlocks = 4;
 
 enum : int8_t
 {
@@ -69,6 +69,7 @@ struct DeviceParams
     int32_t* path_len;           // [n]  number of RLE entries, 0 if none
     uint32_t* metadata;          // [n]  index | is_optimal << 31
     unsigned long long* cells;   // [1]  executed DP cells (sum over passes of band_width x target_size)
+    unsigned long long* timers;  // [4]  development: cycles of {patterns, score passes, backtrace} summed over alignments + count; or nullptr
 };
 
 __device__ __forceinline__ int32_t ceil_div(int32_t a, int32_t b) { return (a + b - 1) / b; }
@@ -539,69 +540,123 @@ struct SkewGlobalLoader
     }
 };
 
-// Backtrace accessor on the block records: 32 columns x 3 blocks around the walk in shared memory (the walk only moves up and
-// to the left: within 32 columns it stays inside two blocks, the third serves the scores taken from the block above)
+// Backtrace accessor on the block records: 32 columns x 4 blocks around the walk in shared memory. The walk only moves up and
+// to the left and a step reads at most 33 rows above its own: rows [r - 34, r] lie in two blocks, which must be among the
+// three lower ones of the stage; the fourth serves the scores that a block reaching below the band takes from the block above.
 struct SkewStage
 {
     skew::Geom g;
     const uint4* rec;
-    uint4* s_pm;  // [kSkewStageBlocks][kSkewStageCols] {pv, mv}
-    int32_t* s_S; // [kSkewStageBlocks][kSkewStageCols]
+    uint4* s_pm;  // [2][kSkewStageBlocks][kSkewStageCols] {pv, mv}: the window the walk is in, and the prefetched next one
+    int32_t* s_S; // [2][kSkewStageBlocks][kSkewStageCols]
     int32_t jlo, jhi; // staged columns [jlo, jhi]; jhi < jlo => nothing staged
-    int32_t bhi;      // staged blocks [bhi - 2, bhi]
+    int32_t bhi;      // staged blocks [bhi - 3, bhi]
+    int32_t cur;      // buffer of the current window
+    int32_t pf_jhi, pf_bhi; // window on its way into the other buffer (pf_jhi < 0: none)
     static constexpr bool use_smem = true;
+    static constexpr int32_t kBuf  = kSkewStageBlocks * kSkewStageCols;
 
+    __device__ __forceinline__ bool covers(int32_t r, int32_t b_hi) const { return (r >> 6) <= b_hi && r - 34 >= 64 * (b_hi - 2); }
     __device__ __forceinline__ bool need(int32_t i, int32_t j) const
     {
         if (jhi < jlo || j - 1 < jlo || j > jhi)
             return true;
-        const int32_t r = g.top(j) + i - 1;
-        return (r >> 6) > bhi || (bhi > 2 && r - 34 < 64 * (bhi - 2));
+        return !covers(g.top(j) + i - 1, bhi);
+    }
+    // the 16 + 4 bytes of block B, column c: where they are in the records
+    __device__ __forceinline__ const uint4* pm_src(int32_t B, int32_t c) const { return rec + skew::chunk_index(g, B, c, c % skew::kK); }
+    __device__ __forceinline__ const int32_t* s_src(int32_t B, int32_t c) const
+    {
+        return reinterpret_cast<const int32_t*>(rec + skew::chunk_index(g, B, c, skew::kK + (c % skew::kK) / 4)) + (c % skew::kK) % 4;
     }
     __device__ __forceinline__ void refill(int32_t i, int32_t j, int32_t lane)
     {
         __syncwarp();
-        jhi             = j;
-        jlo             = max(0, j - kSkewStageCols + 1);
         const int32_t r = max(0, g.top(j) + i - 1);
-        bhi             = min(r >> 6, g.last_block);
-        const int32_t c = jlo + lane;
-        if (c <= jhi)
+        if (pf_jhi >= 0)
         {
+            asm volatile("cp.async.wait_all;" ::: "memory"); // the prefetch has landed (or is dropped: nothing is in flight below)
+            __syncwarp();
+        }
+        if (pf_jhi == j && covers(r, pf_bhi))
+        {
+            // the walk arrived where the prefetch expected it: switch buffers
+            cur ^= 1;
+            jhi = j;
+            jlo = max(0, j - kSkewStageCols + 1);
+            bhi = pf_bhi;
+        }
+        else
+        {
+            jhi             = j;
+            jlo             = max(0, j - kSkewStageCols + 1);
+            bhi             = min(r >> 6, g.last_block);
+            const int32_t c = min(jlo + lane, jhi); // lanes beyond the last column repeat it (their slots are never read)
+            // all loads first (one 16-byte and one 4-byte load per block), then the stores
+            uint4 pm[kSkewStageBlocks];
+            int32_t sc[kSkewStageBlocks];
 #pragma unroll
             for (int32_t b = 0; b < kSkewStageBlocks; b++)
             {
-                const int32_t B = bhi - (kSkewStageBlocks - 1) + b;
-                if (B >= 0)
-                {
-                    s_pm[b * kSkewStageCols + lane] = rec[skew::chunk_index(g, B, c, c % skew::kK)];
-                    s_S[b * kSkewStageCols + lane] =
-                        reinterpret_cast<const int32_t*>(rec + skew::chunk_index(g, B, c, skew::kK + (c % skew::kK) / 4))[(c % skew::kK) % 4];
-                }
+                const int32_t B = max(0, bhi - (kSkewStageBlocks - 1) + b);
+                pm[b]           = *pm_src(B, c);
+                sc[b]           = *s_src(B, c);
             }
+#pragma unroll
+            for (int32_t b = 0; b < kSkewStageBlocks; b++)
+            {
+                s_pm[cur * kBuf + b * kSkewStageCols + lane] = pm[b];
+                s_S[cur * kBuf + b * kSkewStageCols + lane]  = sc[b];
+            }
+        }
+        // The next window on the way while the walk is in this one (asynchronous copies, global -> shared): the walk reaches
+        // column jlo about 31 rows higher (a diagonal; insertions and deletions shift that by a few rows, which the four
+        // staged blocks absorb).
+        pf_jhi = -1;
+        if (jlo > 0)
+        {
+            pf_jhi              = jlo;
+            pf_bhi              = min(max(r - 8, 0) >> 6, g.last_block);
+            const int32_t plo   = max(0, pf_jhi - kSkewStageCols + 1);
+            const int32_t c     = min(plo + lane, pf_jhi);
+            const int32_t other = (cur ^ 1) * kBuf;
+#pragma unroll
+            for (int32_t b = 0; b < kSkewStageBlocks; b++)
+            {
+                const int32_t B = max(0, pf_bhi - (kSkewStageBlocks - 1) + b);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(&s_pm[other + b * kSkewStageCols + lane])),
+                             "l"(__cvta_generic_to_global(pm_src(B, c)))
+                             : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(&s_S[other + b * kSkewStageCols + lane])),
+                             "l"(__cvta_generic_to_global(s_src(B, c)))
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
         __syncwarp();
     }
-    // loader interface of skew::score_at; anything outside the stage comes from global memory (never wrong, only slower)
-    __device__ __forceinline__ void pvmv(int32_t B, int32_t j, uint64_t& pv, uint64_t& mv) const
+    // D(i, j) = get_myers_score (myers_gpu.cu:243-255) on the staged records: skew::score_at without branches (the lanes of a
+    // speculative run sit on different sides of the band's lower edge)
+    __device__ __forceinline__ int32_t get(int32_t i, int32_t j) const
     {
-        const int32_t b = B - (bhi - (kSkewStageBlocks - 1));
-        uint4 v;
-        if (b >= 0 && b < kSkewStageBlocks && j >= jlo && j <= jhi)
-            v = s_pm[b * kSkewStageCols + (j - jlo)];
-        else
-            v = rec[skew::chunk_index(g, B, j, j % skew::kK)];
-        pv = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
-        mv = static_cast<uint64_t>(v.z) | (static_cast<uint64_t>(v.w) << 32);
+        const int32_t top    = g.top(j);
+        const int32_t r      = top + i - 1;
+        const int32_t B      = r >> 6;
+        const int32_t b      = r & 63;
+        const bool from_last = 64 * B + 63 <= top + g.bw - 1; // the block's last row is inside the band: count down from its score
+        const int32_t col    = min(max(j - jlo, 0), kSkewStageCols - 1);
+        const int32_t b0     = bhi - (kSkewStageBlocks - 1);
+        const int32_t sb     = min(max(B - b0, 0), kSkewStageBlocks - 1);
+        const int32_t sa     = min(max(B - b0 - (from_last ? 0 : 1), 0), kSkewStageBlocks - 1);
+        const uint4 v        = s_pm[cur * kBuf + sb * kSkewStageCols + col];
+        const int32_t anchor = (!from_last && B == 0) ? j : s_S[cur * kBuf + sa * kSkewStageCols + col];
+        const uint64_t pv    = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
+        const uint64_t mv    = static_cast<uint64_t>(v.z) | (static_cast<uint64_t>(v.w) << 32);
+        const uint64_t lm    = skew::low_mask(b + 1);
+        const uint64_t m     = from_last ? ~lm : lm;
+        const int32_t d      = __popcll(pv & m) - __popcll(mv & m);
+        return from_last ? anchor - d : anchor + d;
     }
-    __device__ __forceinline__ int32_t S(int32_t B, int32_t j) const
-    {
-        const int32_t b = B - (bhi - (kSkewStageBlocks - 1));
-        if (b >= 0 && b < kSkewStageBlocks && j >= jlo && j <= jhi)
-            return s_S[b * kSkewStageCols + (j - jlo)];
-        return reinterpret_cast<const int32_t*>(rec + skew::chunk_index(g, B, j, skew::kK + (j % skew::kK) / 4))[(j % skew::kK) % 4];
-    }
-    __device__ __forceinline__ int32_t get(int32_t i, int32_t j) const { return skew::score_at(g, i, j, *this); }
     __device__ __forceinline__ int32_t first_score(int32_t i, int32_t j) const { return get(i, j); }
     __device__ __forceinline__ void set_band(int32_t) {}
 };
@@ -990,8 +1045,8 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
     constexpr int32_t kStageWords   = kStageCols * kStageStride + 8;
     constexpr int32_t kSkewQ64Words = 4 * kSkewQ64Stride * 2;
     constexpr int32_t kSkewPmOff    = (kSkewQ64Words + kSkewTgtWords + 3) & ~3;
-    constexpr int32_t kSkewSOff     = kSkewPmOff + kSkewStageBlocks * kSkewStageCols * 4;
-    constexpr int32_t kSkewWords    = kSkewSOff + kSkewStageBlocks * kSkewStageCols;
+    constexpr int32_t kSkewSOff     = kSkewPmOff + 2 * kSkewStageBlocks * kSkewStageCols * 4;
+    constexpr int32_t kSkewWords    = kSkewSOff + 2 * kSkewStageBlocks * kSkewStageCols;
     constexpr int32_t kRawWords     = (3 * kStageWords > kSkewWords ? 3 * kStageWords : kSkewWords);
     __shared__ __align__(16) WordType s_raw[kRawWords];
     WordType* const s_pv   = s_raw;
@@ -1037,6 +1092,7 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
         __syncthreads();
         if (a >= P.n_alignments)
             break;
+        const unsigned long long tm0 = P.timers ? clock64() : 0ull;
         const char* const query   = P.seqs + P.seq_starts[2 * a];
         const char* const target  = P.seqs + P.seq_starts[2 * a + 1];
         const int32_t query_size  = static_cast<int32_t>(P.seq_starts[2 * a + 1] - P.seq_starts[2 * a]);
@@ -1134,6 +1190,7 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
         Q.gbase   = qpat;
         Q.n_words = n_words;
 
+        const unsigned long long tm1 = P.timers ? clock64() : 0ull;
         // ---- Ukkonen band doubling (:955-1002), two passes per round
         View<WordType> pvm{pv_ws, 0}, mvm{mv_ws, 0};
         View<int32_t> scm{sc_ws, 0};
@@ -1241,6 +1298,7 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
             if (done)
                 break;
         }
+        const unsigned long long tm2 = P.timers ? clock64() : 0ull;
         if (warp == winner)
         {
             int32_t path_length = 0;
@@ -1261,7 +1319,11 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
                     K.jlo  = 0;
                     K.jhi  = -1;
                     K.bhi  = 0;
+                    K.cur  = 0;
+                    K.pf_jhi = -1;
+                    K.pf_bhi = 0;
                     path_length = backtrace_banded(lane, K, out_actions, out_runs, s_dbeg[warp], s_dend[warp], bw, target_size);
+                    asm volatile("cp.async.wait_all;" ::: "memory"); // a prefetch the walk did not need any more
                 }
                 else
                 {
@@ -1289,6 +1351,13 @@ __global__ void __launch_bounds__(64, 8) myers_banded_kernel(const DeviceParams 
             {
                 P.path_len[a] = path_length;
                 P.metadata[a] = static_cast<uint32_t>(a) | ((band_width > 0) ? (1u << 31) : 0u);
+                if (P.timers)
+                {
+                    atomicAdd(&P.timers[0], tm1 - tm0);
+                    atomicAdd(&P.timers[1], tm2 - tm1);
+                    atomicAdd(&P.timers[2], static_cast<unsigned long long>(clock64()) - tm2);
+                    atomicAdd(&P.timers[3], 1ull);
+                }
             }
         }
         __syncthreads();

@@ -53,8 +53,25 @@ GWB_HD int32_t popc64(uint64_t x)
 #endif
 }
 
-// bits [0, n) set; n <= 0 -> none, n >= 64 -> all
-GWB_HD uint64_t low_mask(int32_t n) { return n <= 0 ? 0ull : (n >= 64 ? ~0ull : ((1ull << n) - 1ull)); }
+// bits [0, n) set; n <= 0 -> none, n >= 64 -> all. Two 32-bit halves, no branches.
+GWB_HD uint32_t low_mask32(int32_t n)
+{
+    // n already clamped to [0, 32]
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0), "r"(n));
+    return r;
+#else
+    return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+#endif
+}
+GWB_HD uint64_t low_mask(int32_t n)
+{
+    const int32_t a = n < 0 ? 0 : (n > 32 ? 32 : n);
+    const int32_t m = n - 32;
+    const int32_t b = m < 0 ? 0 : (m > 32 ? 32 : m);
+    return static_cast<uint64_t>(low_mask32(a)) | (static_cast<uint64_t>(low_mask32(b)) << 32);
+}
 
 struct Geom
 {
@@ -123,80 +140,85 @@ GWB_HD void lane_init(LaneState& L, int32_t B)
     L.B  = B;
 }
 
-// One column (1 <= t <= tsize) of block L.B. eq: match bits of the block's rows against target[t - 1]; hin_recv: horizontal
-// delta of row 64B - 1 (from the lane above); T: D(64B - 1, t). Returns the horizontal delta of row 64B + 63.
-GWB_HD int32_t column(const Geom& g, LaneState& L, int32_t t, uint64_t eq, int32_t hin_recv, int32_t T)
+// One column of block L.B (straight-line code: the lanes of a warp are at different places of the band). eq: match bits of the
+// block's rows against target[t - 1]; in_pos / in_neg: the horizontal delta of row 64B - 1 (from the lane above) is +1 / -1;
+// hold: column 0 of the matrix (eq = 0 and no horizontal delta leave the initial state -- pv all ones -- as it is).
+// out_pos / out_neg: horizontal delta of row 64B + 63. L.S follows that delta.
+GWB_HD void column(const Geom& g, LaneState& L, int32_t t, uint64_t eq, bool in_pos, bool in_neg, bool hold, uint32_t& out_pos, uint32_t& out_neg)
 {
-    const int32_t top   = g.top(t);
-    const int32_t lo    = top - 64 * L.B;  // first bit of the block inside the band (<= 0: from bit 0)
-    const int32_t hi    = lo + g.bw;       // one past the last bit inside the band (>= 64: through bit 63)
-    const uint64_t keep = ~low_mask(lo);   // rows above the band: pv = mv = eq = 0 -> their ph is 1: +1 into the first band row
-    const uint64_t below = ~low_mask(hi);  // rows below the band
+    const int32_t lo     = g.top(t) - 64 * L.B; // first bit of the block inside the band (<= 0: from bit 0)
+    const int32_t hi     = lo + g.bw;           // one past the last bit inside the band (>= 64: through bit 63)
+    const uint64_t keep  = ~low_mask(lo);       // rows above the band: pv = mv = eq = 0 -> their ph is 1: +1 into the first band row
+    const uint64_t below = ~low_mask(hi);       // rows below the band
     // the band's first row takes +1 from above (the block above may already have been retired by its lane)
-    const int32_t hin = lo > 0 ? 0 : (lo == 0 ? 1 : hin_recv);
+    const bool pos = !hold && (lo == 0 || (lo < 0 && in_pos));
+    const bool neg = !hold && lo < 0 && in_neg;
     uint64_t pv = L.pv & keep, mv = L.mv & keep;
     uint64_t e  = eq & keep;
     const uint64_t xv = e | mv;
-    if (hin < 0)
-        e |= 1ull;
+    e |= neg ? 1ull : 0ull;
     const uint64_t xh = (((e & pv) + pv) ^ pv) | e;
     uint64_t ph       = mv | ~(xh | pv);
     uint64_t mh       = pv & xh;
-    const int32_t hout = static_cast<int32_t>(ph >> 63) - static_cast<int32_t>(mh >> 63);
-    ph                 = (ph << 1) | (hin > 0 ? 1ull : 0ull);
-    mh                 = (mh << 1) | (hin < 0 ? 1ull : 0ull);
-    pv                 = mh | ~(xv | ph);
-    mv                 = ph & xv;
+    out_pos           = static_cast<uint32_t>(ph >> 63);
+    out_neg           = static_cast<uint32_t>(mh >> 63);
+    ph                = (ph << 1) | (pos ? 1ull : 0ull);
+    mh                = (mh << 1) | (neg ? 1ull : 0ull);
+    pv                = mh | ~(xv | ph);
+    mv                = ph & xv;
     // rows below the band keep the worst case: the row that enters next finds vertical delta +1 (myers_gpu.cu:721-726)
-    pv |= below;
-    mv &= ~below;
-    L.pv = pv;
-    L.mv = mv;
-    if (hi >= 64)
-    {
-        const int32_t hi_prev = g.top(t - 1) - 64 * L.B + g.bw;
-        if (hi_prev >= 64)
-            L.S += hout;                       // the last row was in the band in column t - 1 as well
-        else
-            L.S = T + popc64(pv) - popc64(mv); // it has just entered: from the row above the block (all 64 rows are in the band)
-    }
-    return hout;
+    L.pv = pv | below;
+    L.mv = mv & ~below;
+    L.S += static_cast<int32_t>(out_pos) - static_cast<int32_t>(out_neg);
 }
 
 // What a lane hands to the lane below after a step
 struct Link
 {
-    uint32_t hbits; // K x 2 bits: horizontal delta of the block's last row + 1
+    uint32_t hbits; // bit k: the horizontal delta of the block's last row in column k of the batch is +1; bit 8 + k: it is -1
     int32_t S0;     // score of the block's last row in the first column of the batch
 };
 
 // One step of a lane: batch cb (columns K cb .. K cb + K - 1) of block L.B. eqs[k]: match bits against target[K cb + k - 1].
-// rec_pvmv[k] = {pv, mv} and rec_S[k] of the K columns, for the record store.
+// rec_pvmv[k] = {pv, mv} and rec_S[k] of the K columns, for the record store. Columns beyond the target run like the others
+// (nobody reads them).
 GWB_HD Link lane_step(const Geom& g, LaneState& L, int32_t cb, const uint64_t* eqs, Link in, uint64_t (*rec_pvmv)[2], int32_t* rec_S)
 {
     Link out;
     out.hbits = 0;
-    out.S0    = 0;
-    int32_t T = (L.B == 0) ? kK * cb : in.S0; // D(64B - 1, K cb): matrix row "-1" is D(0, t) = t
+    const int32_t t0 = kK * cb;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int32_t k = 0; k < kK; k++)
     {
-        const int32_t t        = kK * cb + k;
-        const int32_t hin_recv = static_cast<int32_t>((in.hbits >> (2 * k)) & 3u) - 1;
-        if (k > 0)
-            T += (L.B == 0) ? 1 : hin_recv;
-        int32_t hout = 0;
-        if (t >= 1 && t <= g.tsize)
-            hout = column(g, L, t, eqs[k], hin_recv, T);
-        out.hbits |= static_cast<uint32_t>(hout + 1) << (2 * k);
+        const bool hold = (k == 0) && cb == 0;
+        uint32_t op, on;
+        column(g, L, t0 + k, hold ? 0ull : eqs[k], ((in.hbits >> k) & 1u) != 0u, ((in.hbits >> (8 + k)) & 1u) != 0u, hold, op, on);
+        out.hbits += (op << k) + (on << (8 + k));
         rec_pvmv[k][0] = L.pv;
         rec_pvmv[k][1] = L.mv;
         rec_S[k]       = L.S;
-        if (k == 0)
-            out.S0 = L.S;
     }
+    // The score follows the horizontal delta of the block's last row, which means something only while that row is inside the
+    // band. Once per block the row enters the band (at the bottom, during the diagonal phase): from that column on the score
+    // is the score of the row above the block -- the lane above is exact there: T = its S0 + its deltas -- plus the block's
+    // vertical deltas.
+    const int32_t hi_before = (cb == 0 ? 0 : g.top(t0 - 1)) - 64 * L.B + g.bw;
+    const int32_t hi_last   = g.top(t0 + kK - 1) - 64 * L.B + g.bw;
+    if (hi_before < 64 && hi_last >= 64)
+    {
+        int32_t T = (L.B == 0) ? t0 : in.S0; // D(64B - 1, t0): matrix row "-1" is D(0, t) = t
+        for (int32_t k = 0; k < kK; k++)
+        {
+            if (k > 0)
+                T += (L.B == 0) ? 1 : static_cast<int32_t>((in.hbits >> k) & 1u) - static_cast<int32_t>((in.hbits >> (8 + k)) & 1u);
+            if (g.top(t0 + k) - 64 * L.B + g.bw >= 64)
+                rec_S[k] = T + popc64(rec_pvmv[k][0]) - popc64(rec_pvmv[k][1]);
+        }
+        L.S = rec_S[kK - 1];
+    }
+    out.S0 = rec_S[0];
     return out;
 }
 

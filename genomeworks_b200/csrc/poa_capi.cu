@@ -852,6 +852,8 @@ static int poa_batch_create_impl(gwb200_poa_batch** out, int32_t device_id, void
             e               = std::getenv("GWB200_POA_GROUP"); // development switch: chunks per straight-line group (4, 2, 1)
             // 32-bit scores: 8 cells per lane and chunk, groups of one chunk measured best (C3: 1493 vs 1485 windows/s with two)
             b->Y.max_group  = e ? std::atoi(e) : (b->score32 ? 1 : 2);
+            e               = std::getenv("GWB200_POA_ROW_FENCE"); // development A/B switch: 1 = proxy fence in front of every general row
+            b->Y.row_fence  = (e && std::atoi(e) != 0) ? 1 : 0;
             e               = std::getenv("GWB200_POA_WAVEFRONT");
             b->Y.wavefront  = (e && std::atoi(e) != 0) ? 1 : 0; // off by default until it beats dp_rows_v3 (development switch)
         }

@@ -86,6 +86,7 @@ struct V3Extra
     int32_t tb_tma;        // 1: traceback tiles by bulk asynchronous copies with prefetch (default); 0: lane loads (A/B switch)
     int32_t wavefront;     // 1: 32-bit score rows as a skewed wavefront (poa_kernels_v4.cuh); 0: dp_rows_v3 (default)
     int32_t max_group;     // chunks per straight-line group of the row loop: 4, 2 or 1 (see dp_rows_v3)
+    int32_t row_fence;     // 1: fence.proxy.async in front of every general row that reads rows older than the ring (A/B switch)
 };
 
 // Static shared memory of the v3 kernel that is not part of the pool
@@ -97,6 +98,13 @@ struct V3Shared
     uint32_t pad_[2];
 };
 
+// 1: a chunk whose entering horizontal run dominates all of its cells is decided by one ballot instead of the prefix scan.
+// Measured and left off: the scan runs in ~57 % of the chunks of a wide band (right of the alignment path every cell is its left
+// neighbour + gap), yet the extra ballot on the carry chain costs more than the scans it saves (C3 1456 vs 1503 windows/s, C2
+// 37.3 k vs 38.6 k; profiles/r02_summary.md).
+#ifndef GWB200_V3_PURE
+#define GWB200_V3_PURE 0
+#endif
 #ifndef GWB200_V3_CPL32
 #define GWB200_V3_CPL32 8 // 4: one 16-byte unit per lane and chunk (the round-2 layout, kept as the A/B partner)
 #endif
@@ -323,7 +331,7 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
                 a[j][i] = __viaddmax_s32(a[j][i - 1], gap, a[j][i]);
         }
     }
-    // ---- what the carry resolution needs from the neighbours
+    // ---- what the carry resolution needs from the neighbours (independent of the carry: issued for all chunks at once)
 #pragma unroll
     for (int32_t j = 0; j < NJ; j++)
     {
@@ -333,19 +341,38 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
         s0l0[j]                 = __shfl_sync(kFull, a[j][0], 0);
         need[j]                 = __ballot_sync(kFull, lane > 0 && act[j] && nbraw[j] + gap > a[j][0]);
     }
-    // ---- carries, chunk by chunk (uniform control flow; the scan is rare)
+    // ---- carries, chunk by chunk (uniform control flow)
 #pragma unroll
     for (int32_t j = 0; j < NJ; j++)
     {
         leftv[j] = (lane == 0) ? cleft : nbraw[j];
         if (need[j] != 0u || cin + gap > s0l0[j])
         {
-            // a horizontal run crosses a lane boundary (or enters from the chunk to the left): max-plus prefix scan over the lanes
-            const int32_t L = chunk_scan<CPL>(a[j], cin, gap, lane);
-            if (lane != 0)
-                leftv[j] = L;
             const int32_t last_lane = min(31, (cx.bw - (c0 + j) * CH) / CPL - 1);
-            outv[j]                 = __shfl_sync(kFull, a[j][CPL - 1], last_lane);
+            const int32_t gl        = CPL * gap;
+            // A horizontal run crosses a lane boundary or enters from the chunk to the left. Right of the alignment path every
+            // cell is its left neighbour + gap: the run that enters the chunk dominates all of it (about half of the chunks of
+            // a wide band). The locally closed values satisfy a[i] >= a[i-1] + gap, so "every cell of the lane is dominated"
+            // is one comparison of the lane's last cell and the whole chunk is decided by one ballot; only the remaining
+            // chunks (the one the path crosses) run the max-plus prefix scan over the lanes.
+            const int32_t bound = cin + gl * (lane + 1);
+            if (GWB200_V3_PURE != 0 && __ballot_sync(kFull, act[j] && a[j][CPL - 1] > bound) == 0u)
+            {
+                const int32_t base = bound - gl;
+                if (lane != 0)
+                    leftv[j] = base;
+#pragma unroll
+                for (int32_t i = 0; i < CPL; i++)
+                    a[j][i] = base + (i + 1) * gap;
+                outv[j] = cin + gl * (last_lane + 1);
+            }
+            else
+            {
+                const int32_t L = chunk_scan<CPL>(a[j], cin, gap, lane);
+                if (lane != 0)
+                    leftv[j] = L;
+                outv[j] = __shfl_sync(kFull, a[j][CPL - 1], last_lane);
+            }
         }
         cin   = static_cast<ScoreT>(outv[j]);
         cleft = cin;
@@ -372,7 +399,7 @@ __device__ __forceinline__ void row_group_v3(const RowCtx<ScoreT>& cx, const int
 template <typename ScoreT, typename SizeT, bool BULK>
 __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const uint8_t* __restrict__ read, const Band<ScoreT>& B,
                            const int32_t band_width, const int32_t max_column, const int32_t gap, const int32_t mismatch, const int32_t match,
-                           int4* row_meta, uint8_t* pool, const int32_t pool_bytes, int4* srec, const int32_t max_group)
+                           int4* row_meta, uint8_t* pool, const int32_t pool_bytes, int4* srec, const int32_t max_group, const int32_t row_fence)
 {
     constexpr int32_t kMin   = min_score_of<ScoreT>();
     constexpr int32_t CPL    = V3Cells<ScoreT>::kCPL;
@@ -384,11 +411,13 @@ __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const
     const int32_t rowbytes   = stride * static_cast<int32_t>(sizeof(ScoreT));
     const int32_t nchunks    = (band_width + CH - 1) / CH;
     ScoreT* const ring       = reinterpret_cast<ScoreT*>(pool);
-    int32_t R                = min(pool_bytes / rowbytes, 64);
-    const bool use_ring      = R >= 2;
-    if (!use_ring)
-        R = 1;
-    const bool bulk = BULK && use_ring;
+    // the host sizes the pool for at least two rows of the widest band (v3_pool_bytes): the rows always go through the ring, so
+    // every row access of the fast path is a shared-memory access the compiler can see as one (no generic pointers)
+    const int32_t R          = min(pool_bytes / rowbytes, 64);
+    if (R < 2)
+        __trap(); // only reachable with the development override of the pool size
+    constexpr bool use_ring  = true;
+    constexpr bool bulk      = BULK;
 
     // row 0: scores[j] = j * gap (:269-272), also into ring slot 0
     for (int32_t j = lane; j < stride; j += 32)
@@ -450,7 +479,7 @@ __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const
         for (int32_t k = 0; k < nrows; k++)
         {
             // next group's metadata: three dependent global loads spread over the row iterations
-            if (nvalid)
+            if (nvalid && ((0x10100401u >> k) & 1u) != 0u) // k in {0, 10, 20, 28}
             {
                 if (k == 0)
                 {
@@ -515,8 +544,12 @@ __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const
                     }
                     else
                     {
-                        int32_t penalty = max(kMin, static_cast<int32_t>(prow0[0]));
-                        if (pc == 2)
+                        // local 0 of a predecessor row holds the minimum unless that row's band starts at column 0 (only the
+                        // first rows of a graph): no dependent shared-memory loads in the common case
+                        int32_t penalty = kMin;
+                        if (bs == sh0)
+                            penalty = max(kMin, static_cast<int32_t>(prow0[0]));
+                        if (pc == 2 && bs == sh1)
                             penalty = max(penalty, static_cast<int32_t>(prow1[0]));
                         first = penalty + gap;
                     }
@@ -570,28 +603,37 @@ __device__ void dp_rows_v3(const Win<SizeT>& g, const int32_t graph_count, const
             else
             {
                 // ---- general row: any number of predecessors, rows that left the ring come from global memory
-                if (bulk)
-                {
-                    // rows are made visible in global memory by the bulk copies; everything older than the ring is complete once
-                    // at most min(R, 4) - 1 groups are pending
-                    if (lane == 0)
-                    {
-                        if (R >= 5)
-                            bulk_wait<3>();
-                        else if (R >= 3)
-                            bulk_wait<2>();
-                        else
-                            bulk_wait<1>();
-                        fence_async_all();
-                    }
-                    __syncwarp();
-                }
                 const int4 rm         = row_meta[row];
                 const int32_t node_id = rm.x;
                 const int32_t pcf     = (rm.w >> 8) & 0xff;
                 auto pred_index = [&](int32_t p) -> int32_t {
                     return (p == 0) ? rm.y : (p == 1 ? rm.z : static_cast<int32_t>(g.pos[g.in_edge(node_id, p)]) + 1);
                 };
+                if (bulk)
+                {
+                    // Rows reach global memory by the bulk copies. A row with three or more predecessors that are all still in
+                    // the ring needs none of that; otherwise everything older than the ring is complete once at most
+                    // min(R, 4) - 1 groups are pending (the wait makes the writes visible to the waiting thread -- and
+                    // invalidates the L1 --, the warp barrier orders the other lanes behind it).
+                    int32_t far = 0;
+                    for (int32_t p = 0; p < pcf; p++)
+                        far |= (row - pred_index(p) >= R) ? 1 : 0;
+                    if (far != 0)
+                    {
+                        if (lane == 0)
+                        {
+                            if (R >= 5)
+                                bulk_wait<3>();
+                            else if (R >= 3)
+                                bulk_wait<2>();
+                            else
+                                bulk_wait<1>();
+                            if (row_fence != 0)
+                                fence_async_all();
+                        }
+                        __syncwarp();
+                    }
+                }
                 auto pred_row_ptr = [&](int32_t pi) -> const ScoreT* {
                     const int32_t d = row - pi;
                     if (use_ring && d < R)
@@ -1631,7 +1673,8 @@ template <typename ScoreT, typename SizeT, bool BULK, bool WAVE>
 __device__ int32_t nw_banded_v3(const Win<SizeT>& g, int32_t graph_count, const uint8_t* read, int32_t read_length, ScoreT* scores,
                                 float max_buffer_size, SizeT* aln_graph, SizeT* aln_read, int32_t band_width, int32_t gap, int32_t mismatch,
                                 int32_t match, int32_t rerun, const bool Adaptive, unsigned long long& cells, int4* row_meta, uint8_t* pool,
-                                int32_t pool_bytes, unsigned long long* timers, V3Shared* sh, const int32_t tb_mode, const int32_t wavefront, const int32_t max_group)
+                                int32_t pool_bytes, unsigned long long* timers, V3Shared* sh, const int32_t tb_mode, const int32_t wavefront, const int32_t max_group,
+                                const int32_t row_fence)
 {
     GWB200_TIMER_START();
     const float gradient     = __fdividef(static_cast<float>(read_length + 1), static_cast<float>(graph_count + 1));
@@ -1681,7 +1724,8 @@ __device__ int32_t nw_banded_v3(const Win<SizeT>& g, int32_t graph_count, const 
                                              sh->rec[0]);
     }
     if (!done)
-        dp_rows_v3<ScoreT, SizeT, BULK>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes, sh->rec[0], max_group);
+        dp_rows_v3<ScoreT, SizeT, BULK>(g, graph_count, read, B, band_width, max_column, gap, mismatch, match, row_meta, pool, pool_bytes, sh->rec[0],
+                                        max_group, row_fence);
     GWB200_TIMER_LAP(0);
     int32_t result;
     if (tb_mode != 0 && pool_bytes >= TileBuf<ScoreT>::kBytes * 2)
@@ -1803,7 +1847,7 @@ __device__ void process_window_v3(const DeviceParams& P, const V2Extra& X, const
                 {
                     alen = nw_banded_v3<ScoreT, SizeT, BULK, WAVE>(g, node_count, sequence, seq_len, scores, banded_buffer_size, aln_graph, aln_read,
                                                              P.band_width, P.gap, P.mismatch, P.match, rerun, adaptive, cells, row_meta, pool,
-                                                             X.pool_bytes, timers, sh, Y.tb_tma, Y.wavefront, Y.max_group);
+                                                             X.pool_bytes, timers, sh, Y.tb_tma, Y.wavefront, Y.max_group, Y.row_fence);
                     if (!adaptive || attempt == 1 || !(alen == kShiftLeft || alen == kShiftRight))
                         break;
                     rerun = alen; // rerun with extended and shifted band (cudapoa_kernels.cuh:374-396)
