@@ -217,3 +217,33 @@ def test_reverse_complement_flags_travel_with_the_alignment():
         assert fa[0].replace("-", "") == a.get_query_sequence() and fa[2].replace("-", "") == a.get_target_sequence()
     al.close()
     al2.close()
+
+
+def test_skewed_and_classic_score_passes_give_the_same_alignments(monkeypatch):
+    """The skewed score pass (myers_skew.cuh, bands of >= 128 rows) and the classic one (GWB200_MYERS_SKEW=0) must produce the
+    same alignments as the oracle: query longer / shorter than the target, unrelated sequences (every band up to the clamp),
+    a long insertion, clamped asymmetric bands, the unbanded case, lengths around block and word boundaries."""
+    rng = random.Random(77)
+
+    def seq(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+
+    pairs = []
+    for L in (127, 128, 129, 191, 192, 640, 1000, 2047, 2048, 2049, 4097):
+        a = seq(L)
+        pairs.append((a, mutate(rng, a, max(1, L // 12))))
+        pairs.append((mutate(rng, a, max(1, L // 30)), a))
+    a = seq(3000)
+    pairs.append((a, a[:1200] + seq(700) + a[1200:]))   # long insertion: query shorter than the target
+    pairs.append((a[:900] + seq(500) + a[900:], a))      # long deletion: query longer than the target
+    pairs.append((seq(1500), seq(1400)))                 # unrelated: all passes up to the largest band, not optimal
+    pairs.append((a, a))                                 # identical
+    for max_bw in (130, 256, 800, 1024, 2000):
+        got = {}
+        for skew in ("1", "0"):
+            monkeypatch.setenv("GWB200_MYERS_SKEW", skew)
+            res, cells = run_ours(pairs, max_bw)
+            got[skew] = [(r.status, int(r.is_optimal), r.convert_to_cigar(extended=True)) for r in res], cells
+        assert got["1"] == got["0"], max_bw
+        monkeypatch.setenv("GWB200_MYERS_SKEW", "1")
+        check_against_oracle(pairs, max_bw)
