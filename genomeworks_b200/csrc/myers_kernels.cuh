@@ -509,6 +509,8 @@ __device__ void compute_scores_skew(int32_t lane, const skew::Geom& g, uint4* __
                 uint64_t pm[skew::kK][2];
                 int32_t sc[skew::kK];
                 mine = skew::lane_step(g, L, cb, eqs, in, pm, sc);
+                if (skew::block_in_band(g, L.B, cb))
+                {
 #pragma unroll
                 for (int32_t k = 0; k < skew::kK; k++)
                     dst[k * g.nbl] = make_uint4(static_cast<uint32_t>(pm[k][0]), static_cast<uint32_t>(pm[k][0] >> 32), static_cast<uint32_t>(pm[k][1]),
@@ -517,6 +519,7 @@ __device__ void compute_scores_skew(int32_t lane, const skew::Geom& g, uint4* __
                 for (int32_t k = 0; k < skew::kK; k += 4)
                     dst[(skew::kK + k / 4) * g.nbl] = make_uint4(static_cast<uint32_t>(sc[k]), static_cast<uint32_t>(sc[k + 1]),
                                                                  static_cast<uint32_t>(sc[k + 2]), static_cast<uint32_t>(sc[k + 3]));
+                }
             }
         }
     }
@@ -567,6 +570,8 @@ __device__ void compute_scores_skew_pair(int32_t lane, const skew::Geom& g0, uin
                 uint64_t pm[skew::kK][2];
                 int32_t sc[skew::kK];
                 mine = skew::lane_step(g, L, cb, eqs, in, pm, sc);
+                if (skew::block_in_band(g, L.B, cb))
+                {
 #pragma unroll
                 for (int32_t k = 0; k < skew::kK; k++)
                     dst[k * g.nbl] = make_uint4(static_cast<uint32_t>(pm[k][0]), static_cast<uint32_t>(pm[k][0] >> 32), static_cast<uint32_t>(pm[k][1]),
@@ -575,6 +580,7 @@ __device__ void compute_scores_skew_pair(int32_t lane, const skew::Geom& g0, uin
                 for (int32_t k = 0; k < skew::kK; k += 4)
                     dst[(skew::kK + k / 4) * g.nbl] = make_uint4(static_cast<uint32_t>(sc[k]), static_cast<uint32_t>(sc[k + 1]),
                                                                  static_cast<uint32_t>(sc[k + 2]), static_cast<uint32_t>(sc[k + 3]));
+                }
             }
         }
     }

@@ -222,6 +222,13 @@ GWB_HD Link lane_step(const Geom& g, LaneState& L, int32_t cb, const uint64_t* e
     return out;
 }
 
+// Does block B have a row inside the band in some column of batch cb? (only then anybody reads its records: a lane that has
+// moved on to its next block runs a number of batches before the band arrives there)
+GWB_HD bool block_in_band(const Geom& g, int32_t B, int32_t cb)
+{
+    return g.top(kK * cb) <= 64 * B + 63 && g.top(kK * cb + kK - 1) + g.bw - 1 >= 64 * B;
+}
+
 // Does the lane leave its block before batch cb? (the block lies above the band from the first column of the batch on)
 GWB_HD bool block_retired(const Geom& g, int32_t B, int32_t cb) { return g.top(kK * cb) > 64 * B + 63; }
 

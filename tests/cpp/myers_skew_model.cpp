@@ -88,6 +88,8 @@ void run_model(const Geom& g, const std::string& q, const std::string& t, Record
             uint64_t rec[kK][2];
             int32_t recS[kK];
             next[l] = lane_step(g, L[l], cb, eqs, in, rec, recS);
+            if (!block_in_band(g, L[l].B, cb))
+                continue; // the kernel does not store these records (nobody may read them: the slots keep 0xdeadbeef)
             for (int32_t k = 0; k < kK; k++)
             {
                 const int64_t c = chunk_index(g, L[l].B, kK * cb + k, k) * 4;
