@@ -925,18 +925,20 @@ __device__ int32_t backtrace_banded(int32_t lane, StageT& S, int8_t* path, int32
             // speculative run of diagonal steps (band row i fixed, j decreasing): lane k evaluates the step at column j - k on the
             // staged columns; the leading lanes whose step is "neither insertion nor deletion" are exactly the serial steps.
             const int32_t jk = j - lane;
-            bool ok          = jk >= diagonal_begin && (jk - 1) >= S.jlo;
-            int32_t my = 0, dg = 0;
-            if (ok)
+            const bool ev    = jk >= diagonal_begin && (jk - 1) >= S.jlo;
+            bool ok          = ev;
+            int32_t my = 0, dg = 0, above = kOutOfBand, left = kOutOfBand;
+            if (ev)
             {
-                my                  = S.get(i, jk);
-                dg                  = S.get(i, jk - 1);
-                const int32_t above = i <= 1 ? kOutOfBand : S.get(i - 1, jk);
-                const int32_t left  = i >= band_width ? kOutOfBand : S.get(i + 1, jk - 1);
-                ok                  = (left + 1 != my) && (above + 1 != my);
+                my    = S.get(i, jk);
+                dg    = S.get(i, jk - 1);
+                above = i <= 1 ? kOutOfBand : S.get(i - 1, jk);
+                left  = i >= band_width ? kOutOfBand : S.get(i + 1, jk - 1);
+                ok    = (left + 1 != my) && (above + 1 != my);
             }
-            uint32_t okmask = __ballot_sync(kFull, ok);
-            if (__shfl_sync(kFull, my, 0) != myscore)
+            uint32_t okmask   = __ballot_sync(kFull, ok);
+            const int32_t my0 = __shfl_sync(kFull, my, 0);
+            if (my0 != myscore)
                 okmask = 0u; // the walk carries an implicit (worst-case) value here, not the matrix entry: take the serial step
             const int32_t run = (okmask == kFull) ? 32 : (__ffs(~okmask) - 1);
             if (run > 0)
@@ -945,6 +947,37 @@ __device__ int32_t backtrace_banded(int32_t lane, StageT& S, int8_t* path, int32
                 rle_append_diagonal_run(W, mm, run);
                 myscore = __shfl_sync(kFull, dg, run - 1);
                 j -= run;
+                continue;
+            }
+            if ((__ballot_sync(kFull, ev) & 1u) != 0u && my0 == myscore)
+            {
+                // an insertion or deletion right here: lane 0 has evaluated exactly what the serial step below would (same cells,
+                // same implicit values), take its neighbours instead of fetching them again
+                const int32_t left0  = __shfl_sync(kFull, left, 0);
+                const int32_t above0 = __shfl_sync(kFull, above, 0);
+                const int32_t dg0    = __shfl_sync(kFull, dg, 0);
+                int32_t r;
+                if (left0 + 1 == myscore)
+                {
+                    r       = st_insertion;
+                    myscore = left0;
+                    ++i;
+                    --j;
+                }
+                else if (above0 + 1 == myscore)
+                {
+                    r       = st_deletion;
+                    myscore = above0;
+                    --i;
+                }
+                else
+                {
+                    r       = (dg0 == myscore ? st_match : st_mismatch);
+                    myscore = dg0;
+                    --j;
+                }
+                W.change(r);
+                ++W.r_count;
                 continue;
             }
         }
