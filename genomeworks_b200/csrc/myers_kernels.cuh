@@ -1,14 +1,19 @@
-// gw-b200 banded Myers / Ukkonen global aligner, device code (sm_100a). One alignment per warp, persistent CTAs.
+// gw-b200 banded Myers / Ukkonen global aligner, device code (sm_100a). One alignment per CTA of two warps (the pass of the
+// current Ukkonen estimate and, speculatively, the pass of the doubled one), persistent CTAs, atomic work counter.
 //
 // Behavioural contract = the reference's myers_banded_kernel and callees (cudaaligner/src/myers_gpu.cu:78-255, 444-1032):
-// identical band choices, identical bit-vector band (pv / mv / score per 32-row word and target column, including the
-// worst-case fills at the band edges), identical backtrace tie-breaking (insertion, deletion, then diagonal) and RLE path.
+// identical band choices, identical edit-distance values for every cell of the band (including the worst-case assumptions at
+// the band edges), identical backtrace tie-breaking (insertion, deletion, then diagonal) and RLE path.
 // The implementation is not the reference's:
-//   * for bands of <= 32 words (max_bandwidth <= 1024) column t-1 lives in registers: the hot loop issues no loads of
-//     pv/mv/score, only three coalesced 128-byte stores per column (12 B per word-column = the algorithmic bytes);
-//   * the multi-word addition resolves its carries with two warp ballots and one integer add instead of a shuffle loop;
-//   * the backtrace runs out of shared memory: the warp stages 32 target columns x band words with coalesced loads and
-//     walks them with popcount score reconstruction, instead of ~9 dependent global loads per step on one lane;
+//   * score pass, bands of >= 128 rows: the skewed formulation of myers_skew.cuh -- lane = 64-row block of the query, K columns
+//     per step on registers, the only cross-lane traffic two shuffles per K columns, records [step][chunk][lane] so that the
+//     stores of a step are contiguous across the lanes (compute_scores_skew);
+//   * score pass, other bands: lane = word of the band; for <= 32 words column t-1 lives in registers (three coalesced 128-byte
+//     stores per column, no loads), the multi-word addition resolves its carries with two warp ballots and one integer add
+//     instead of a shuffle loop (compute_scores_banded);
+//   * the backtrace (one templated walk) runs out of shared memory: 32 columns around the walk staged by TMA bulk copies on an
+//     mbarrier (classic layout) or by cp.async with the next window prefetched (block records), popcount score reconstruction,
+//     speculative runs of diagonal steps verified by 32 lanes at once;
 //   * results are written to per-alignment slots, then compacted in input order (no atomics, no sort).
 #pragma once
 
