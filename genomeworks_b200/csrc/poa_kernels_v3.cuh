@@ -1,4 +1,4 @@
-// gw-b200 POA device code, third generation (sm_100a): one warp per window, persistent CTAs, 16-byte score units.
+// gw-b200 POA device code, third generation (sm_100a): one warp per window, persistent CTAs, 8 score cells per lane and chunk.
 //
 // Same behavioural contract as poa_kernels.cuh / poa_kernels_v2.cuh (identical consensus / coverage / MSA / status to the
 // reference kernels, cudapoa/src/cudapoa_kernels.cuh:76-542). What changed against v2, and why (profiles/r01_*: 59 % of the
@@ -7,12 +7,14 @@
 //   scheduling   one warp owns one window from the first read to the consensus; the grid is persistent (resident CTAs pull
 //                window indices from an atomic counter), so every resident warp always has work of its own, no CTA barrier
 //                exists anywhere, and batches that are not a multiple of the residency do not pay a wave quantum.
-//   DP rows      every lane owns one 16-byte unit of the row per chunk (4 int32 or 8 int16 cells; the int16 rows leave as
-//                8-wide 16-byte vectors). Chunks are taken left to right with the horizontal carry passed on directly (no
-//                two-phase fold). The predecessor rows are read as one LDS.128 per lane from a shared-memory ring of the most
-//                recent rows, the value beyond the unit comes from the right neighbour by shuffle (no bank-conflicting
-//                scalar load), per-row graph metadata is prepared 32 rows ahead by the lanes and handed over as one 16-byte
-//                shared-memory record per row.
+//   DP rows      every lane owns 8 cells of the row per chunk of 256 columns (int16: one 16-byte unit, the rows leave as 8-wide
+//                vectors; int32: two units), so that the per-chunk costs are paid once per 256 columns. Chunks are taken left
+//                to right with the horizontal carry passed on directly (no two-phase fold). The predecessor rows are read as
+//                LDS.128 from a shared-memory ring of the most recent rows (always: the host sizes the pool for it), the
+//                value beyond the unit comes from the right neighbour by shuffle (no bank-conflicting scalar load), the
+//                substitution test is one xor per four read characters and one predicate-producing logic op per cell,
+//                per-row graph metadata is prepared 32 rows ahead by the lanes and handed over as one 16-byte shared-memory
+//                record per row.
 //   write-back   the finished row is written once into its ring slot and leaves for HBM as ONE bulk asynchronous copy
 //                (cp.async.bulk.global.shared::cta, bulk-group completion) issued by lane 0: the lanes issue no global
 //                stores in the row loop, and the ring slot is reused only after its bulk read has completed.
