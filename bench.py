@@ -7,7 +7,9 @@ of this workload on both this engine and the reference (SURVEY.md fact 3 / DESIG
 which all windows succeed; the factor only sizes the per-window score slab, results are identical). One "step" = one pass of the
 hot path over one batch: as many windows as the Batch holds in HBM (capacity-sized, not rounded to a wave: the kernel runs a
 persistent grid). Windows shard embarrassingly: every rank owns a Batch and its own windows (weak scaling), NCCL is used only
-for the barrier / max-over-ranks timing and the result gather after the timed region (--scaling strong: scatter + gather inside).
+for the barrier and the max-over-ranks timing. (A fixed window list scattered from rank 0 and gathered back in input order over NCCL
+is genomeworks_b200/sharding.py: sharded_consensus, proven against the single-GPU output by tests/test_gpu_sharded.py; it is not a
+bench mode.)
 
   value : windows/s, inputs packed and resident in HBM before the timed region (K x launch, CUDA events on the batch stream,
           max over ranks)
